@@ -1,0 +1,367 @@
+// dev_shade.cuh — textures, light PDFs / sampling, BSDF scatter and the
+// per-vertex weight of the reference's integrator.
+//
+// Reference: internal/hittable/texture.go, perlin.go, materials.go, pdf.go,
+// onb.go, objects.go:52-80,152-165,356-385 (light PdfValue/Random),
+// hittable.go:89-103 (HittableList.PdfValue/Random), vec/vec.go:136-186,
+// camera/camera.go:256-290 (getRay), :319-330 (mixture weighting).
+#pragma once
+#include "dev_trace.cuh"
+
+namespace grtd {
+
+// ---- Perlin noise, perlin.go:34-111 ----------------------------------------
+__device__ __forceinline__ float perlin_noise(const GrtPerlin* P, f3 p) {
+    float fx = floorf(p.x), fy = floorf(p.y), fz = floorf(p.z);
+    float u = p.x - fx, v = p.y - fy, w = p.z - fz;
+    int i = (int)fx, j = (int)fy, k = (int)fz;
+    float uu = u * u * (3 - 2 * u), vv = v * v * (3 - 2 * v), ww = w * w * (3 - 2 * w);
+    float acc = 0.0f;
+#pragma unroll
+    for (int di = 0; di < 2; di++)
+#pragma unroll
+        for (int dj = 0; dj < 2; dj++)
+#pragma unroll
+            for (int dk = 0; dk < 2; dk++) {
+                uint32_t h = P->perm[0][(i + di) & 255] ^ P->perm[1][(j + dj) & 255] ^ P->perm[2][(k + dk) & 255];
+                float4 g = __ldg((const float4*)&P->grad[h][0]);
+                float wx = u - (float)di, wy = v - (float)dj, wz = w - (float)dk;
+                acc += ((di ? uu : 1 - uu) * (dj ? vv : 1 - vv) * (dk ? ww : 1 - ww)) * (g.x * wx + g.y * wy + g.z * wz);
+            }
+    return acc;
+}
+__device__ __forceinline__ float perlin_turbulence(const GrtPerlin* P, f3 p, int depth) {  // perlin.go:57-69
+    float accum = 0.0f, weight = 1.0f;
+    for (int i = 0; i < depth; i++) {
+        accum += weight * perlin_noise(P, p);
+        weight *= 0.5f;
+        p = p * 2.0f;
+    }
+    return fabsf(accum);
+}
+
+// ---- Texture.Value, texture.go:25,50,70,112 ----------------------------------
+template <uint32_t FEAT>
+__device__ __forceinline__ f3 texture_value(const SceneView& sv, uint32_t tex, float u, float v, f3 p) {
+    const GrtTexture* T = sv.textures() + tex;
+    if (FEAT & F_TEXTURE) {
+        // checkerboards may nest (even/odd are textures): walk down
+        for (int guard = 0; guard < 8 && T->type == GRT_TEX_CHECKER; guard++) {  // texture.go:50-59
+            int x = (int)floorf(T->scale * p.x), y = (int)floorf(T->scale * p.y), z = (int)floorf(T->scale * p.z);
+            T = sv.textures() + (((x + y + z) % 2 == 0) ? T->even : T->odd);
+        }
+        if (T->type == GRT_TEX_IMAGE) {  // texture.go:70-91, imageLoader.go:52-62
+            const GrtImage im = sv.images()[T->aux];
+            if (im.height == 0) return mk3(0, 1, 1);
+            float uu = fabsf(fmodf(u, 1.0f));
+            float vv = 1.0f - fabsf(fmodf(v, 1.0f));
+            int i = (int)(uu * (float)(im.width - 1));
+            int j = (int)(vv * (float)(im.height - 1));
+            i = min(max(i, 0), (int)im.width); j = min(max(j, 0), (int)im.height);
+            size_t idx = (size_t)j * im.width + i;
+            if (idx >= (size_t)im.width * im.height) return mk3(1, 0, 1);  // magenta past the end
+            const uint8_t* px = sv.ds->texels + im.offset + idx * 3;
+            const float s = 1.0f / 255.0f;
+            return mk3((float)px[0] * s, (float)px[1] * s, (float)px[2] * s);
+        }
+        if (T->type == GRT_TEX_NOISE) {  // texture.go:112-125
+            const GrtPerlin* P = sv.ds->perlins + (T->aux & 0xFFFFu);
+            uint32_t variant = T->aux >> 16;
+            if (variant == GRT_NOISE_MARBLE) {
+                float s = 0.5f * (1.0f + sinf(T->scale * p.z + 10.0f * perlin_turbulence(P, p, 7)));
+                return mk3(s, s, s);
+            }
+            if (variant == GRT_NOISE_TURBULENT) {
+                float s = perlin_turbulence(P, p, 7);
+                return mk3(s, s, s);
+            }
+            float s = 0.5f * (1.0f + perlin_noise(P, p * T->scale));
+            return mk3(s, s, s);
+        }
+    }
+    return mk3(T->color[0], T->color[1], T->color[2]);
+}
+// does evaluating this material's texture need the sphere's (u,v)?
+template <uint32_t FEAT>
+__device__ __forceinline__ bool material_needs_uv(const SceneView& sv, const GrtMaterial& m) {
+    if (!(FEAT & F_TEXTURE)) return false;
+    if (m.type == GRT_MAT_METAL || m.type == GRT_MAT_DIELECTRIC) return false;
+    uint32_t t = sv.textures()[m.tex].type;
+    return t == GRT_TEX_IMAGE || t == GRT_TEX_CHECKER;  // a checker may contain an image
+}
+
+// ---- orthonormal basis, onb.go:13-43 (fp32 and fp64) --------------------------
+struct Onb {
+    f3 u, v, w;
+};
+__device__ __forceinline__ Onb make_onb(f3 n) {
+    Onb b;
+    b.w = unit(n);
+    f3 a = fabsf(n.x) > 0.9f ? mk3(0, 1, 0) : mk3(1, 0, 0);
+    b.v = unit(cross(n, a));
+    b.u = unit(cross(n, b.v));
+    return b;
+}
+__device__ __forceinline__ f3 onb_transform(const Onb& b, f3 v) { return b.u * v.x + b.v * v.y + b.w * v.z; }
+
+__device__ __forceinline__ d3 unit64(d3 a) { return a * (1.0 / sqrt(dot(a, a))); }
+
+// ---- light Random / PdfValue in fp64 ----------------------------------------
+// The reference samples a light point and then RE-INTERSECTS the light to get
+// its pdf (objects.go:52-62,152-160,356-367).  A sample on the light's edge
+// must not be lost to rounding (a zero pdf with a below-horizon direction is
+// 0/0 = NaN and blacks the pixel, color.go:28-36), so this arithmetic stays in
+// fp64 like the reference; it is ~1 light evaluation per diffuse vertex.
+template <uint32_t FEAT>
+__device__ __forceinline__ d3 light_random(const GrtLight* L, d3 origin, float r1, float r2) {
+    if ((FEAT & F_QUAD_LIGHT) && L->type == GRT_LIGHT_QUAD) {  // objects.go:161-165
+        d3 Q = ldd3(L->p), u = ldd3(L->p + 3), v = ldd3(L->p + 6);
+        d3 p = Q + u * (double)r1 + v * (double)r2;
+        return p - origin;
+    }
+    if ((FEAT & F_SPHERE_LIGHT) && L->type == GRT_LIGHT_SPHERE) {  // objects.go:63-80
+        d3 dir = ldd3(L->p) - origin;
+        double distSquared = dot(dir, dir);
+        double R = L->p[3];
+        // NewONB(direction)
+        d3 w = unit64(dir);
+        d3 a = fabs(dir.x) > 0.9 ? mkd3(0, 1, 0) : mkd3(1, 0, 0);
+        d3 vv = unit64(cross(dir, a));
+        d3 uu = unit64(cross(dir, vv));
+        double z = 1 + (double)r2 * (sqrt(1 - R * R / distSquared) - 1);
+        double phi = 2 * GRT_PI_D * (double)r1;
+        double t = sqrt(1 - z * z);
+        double sn, cs;
+        sincos(phi, &sn, &cs);
+        double x = cs * t, y = sn * t;
+        return uu * x + vv * y + w * z;
+    }
+    if ((FEAT & F_TRI_LIGHT) && L->type == GRT_LIGHT_TRI) {  // objects.go:369-385
+        double a1 = (double)r1;
+        double a2 = (double)r2 * (1 - a1);
+        double a = 1 - a1 - a2;
+        d3 p = ldd3(L->p) * a + ldd3(L->p + 3) * a1 + ldd3(L->p + 6) * a2;
+        return p - origin;
+    }
+    return mkd3(1, 0, 0);  // defaultPdfImpl.Random, hittable.go:73-75
+}
+
+template <uint32_t FEAT>
+__device__ __forceinline__ double light_pdf(const GrtLight* L, d3 o, d3 d) {
+    if ((FEAT & F_QUAD_LIGHT) && L->type == GRT_LIGHT_QUAD) {  // objects.go:152-160 + quad.Hit
+        d3 n = ldd3(L->p + 9);
+        double denom = dot(n, d);
+        if (fabs(denom) < 1e-8) return 0;
+        double t = (L->p[15] - dot(n, o)) / denom;
+        if (!(0.001 <= t)) return 0;
+        d3 Q = ldd3(L->p), u = ldd3(L->p + 3), v = ldd3(L->p + 6), w = ldd3(L->p + 12);
+        d3 planar = (o + d * t) - Q;
+        double alpha = dot(w, cross(planar, v));
+        double beta = dot(w, cross(u, planar));
+        if (!(0 <= alpha && alpha <= 1) || !(0 <= beta && beta <= 1)) return 0;
+        double dd = dot(d, d);
+        double distSquared = t * t * dd;
+        double cosine = fabs(denom / sqrt(dd));
+        return distSquared / (cosine * L->p[16]);
+    }
+    if ((FEAT & F_SPHERE_LIGHT) && L->type == GRT_LIGHT_SPHERE) {  // objects.go:52-62 + sphere.Hit at time 0
+        d3 oc = ldd3(L->p) - o;
+        double R = L->p[3];
+        double a = dot(d, d), h = dot(d, oc), c = dot(oc, oc) - R * R;
+        double disc = h * h - a * c;
+        if (disc < 0) return 0;
+        double sq = sqrt(disc);
+        double root = (h - sq) / a;
+        if (!(0.0001 < root)) {
+            root = (h + sq) / a;
+            if (!(0.0001 < root)) return 0;
+        }
+        double distSquared = dot(oc, oc);
+        double cosThetaMax = sqrt(1 - R * R / distSquared);
+        double solidAngle = 2 * GRT_PI_D * (1 - cosThetaMax);
+        return 1 / solidAngle;
+    }
+    if ((FEAT & F_TRI_LIGHT) && L->type == GRT_LIGHT_TRI) {  // objects.go:356-367 + Triangle.Hit
+        d3 v0 = ldd3(L->p), e0 = ldd3(L->p + 3) - v0, e1 = ldd3(L->p + 6) - v0;
+        d3 pvec = cross(d, e1);
+        double det = dot(e0, pvec);
+        if (fabs(det) < 1e-8) return 0;
+        double invDet = 1.0 / det;
+        d3 tvec = o - v0;
+        double u = dot(tvec, pvec) * invDet;
+        if (u < 0 || u > 1) return 0;
+        d3 qvec = cross(tvec, e0);
+        double v = dot(d, qvec) * invDet;
+        if (v < 0 || (u + v) > 1) return 0;
+        double tl = dot(e1, qvec) * invDet;
+        if (tl < 0.001) return 0;
+        d3 nrm;
+        if (L->flags & GRT_TRI_HAS_NORMALS) {
+            double w = 1.0 - u - v;
+            nrm = unit64(ldd3(L->p + 10) * w + ldd3(L->p + 13) * u + ldd3(L->p + 16) * v);
+        } else {
+            nrm = unit64(cross(e0, e1));
+        }
+        double dd = dot(d, d);
+        double distSquared = tl * tl * dd;
+        double cosine = fabs(dot(d, nrm) / sqrt(dd));
+        return distSquared / (cosine * L->p[9]);
+    }
+    return 0;
+}
+
+// ---- vec.go sampling routines -------------------------------------------------
+__device__ __forceinline__ f3 random_unit_vector(Rng& rng) {  // vec.go:159-167
+    for (;;) {
+        float x = -1.0f + 2.0f * rng.next(), y = -1.0f + 2.0f * rng.next(), z = -1.0f + 2.0f * rng.next();
+        float l2 = x * x + y * y + z * z;
+        if (1e-30f < l2 && l2 <= 1.0f) { float s = 1.0f / sqrtf(l2); return mk3(x * s, y * s, z * s); }
+    }
+}
+__device__ __forceinline__ f3 random_cosine_direction(float r1, float r2) {  // vec.go:177-186
+    float phi = 2 * GRT_PI_F * r1;
+    float sn, cs;
+    sincosf(phi, &sn, &cs);
+    float sr = sqrtf(r2);
+    return mk3(cs * sr, sn * sr, sqrtf(1 - r2));
+}
+__device__ __forceinline__ f3 reflect(f3 v, f3 n) { return v - n * (dot(n, v) * 2); }  // vec.go:136
+__device__ __forceinline__ f3 refract(f3 v, f3 n, float eta) {                           // vec.go:141-146
+    float cosTheta = fminf(dot(-v, n), 1.0f);
+    f3 rPerp = (v + n * cosTheta) * eta;
+    f3 rPar = n * (-sqrtf(fabsf(1.0f - len2(rPerp))));
+    return rPerp + rPar;
+}
+
+// ---- camera ray, camera.go:256-290 ----------------------------------------------
+struct DevCamera {
+    f3 center, p00_rel, du, dv, defu, defv;   // p00_rel = pixel00Loc - center (fp64 difference, rounded once)
+    f3 background;
+    float max_contribution, recip_spp_sqrt, defocus_angle;
+    int width, height, spp_sqrt, max_depth;
+};
+template <uint32_t FEAT>
+__device__ __forceinline__ void camera_ray(const DevCamera& cam, int px, int py, uint32_t sample, uint32_t pixel_index, uint32_t k0, uint32_t k1,
+                                           f3& o, f3& d, float& time) {
+    Rng rng;
+    rng.init(pixel_index, sample, 0, GRT_STREAM_CAMERA, k0, k1);
+    // renderRow calls getRay(j, row, s_j, s_i) (camera.go:97-99): the x stratum is the inner loop index
+    int s_x = (int)(sample % (uint32_t)cam.spp_sqrt), s_y = (int)(sample / (uint32_t)cam.spp_sqrt);
+    float ox = (((float)s_x + rng.next()) * cam.recip_spp_sqrt) - 0.5f;   // sampleSquareStratified :277-282
+    float oy = (((float)s_y + rng.next()) * cam.recip_spp_sqrt) - 0.5f;
+    f3 rel = cam.p00_rel + cam.du * ((float)px + ox) + cam.dv * ((float)py + oy);   // pixelSample - center
+    o = cam.center;
+    if ((FEAT & F_DEFOCUS) && cam.defocus_angle > 0) {   // defocusDiskSample :285-290, RandomUnitDisk vec.go:149-156
+        float dx, dy;
+        for (;;) {
+            dx = -1.0f + 2.0f * rng.next(); dy = -1.0f + 2.0f * rng.next();
+            if (dx * dx + dy * dy < 1.0f) break;
+        }
+        f3 off = cam.defu * dx + cam.defv * dy;
+        o = cam.center + off;
+        rel = rel - off;
+    }
+    d = rel;
+    time = rng.next();   // camera.go:268
+}
+
+// ---- one shading vertex ------------------------------------------------------------
+// Outcome of Material.Scatter + the PDF mixture of camera.go:312-328.
+enum ShadeKind { SHADE_TERMINATE = 0, SHADE_SPECULAR = 1, SHADE_DIFFUSE = 2, SHADE_NAN = 3 };
+struct ShadeResult {
+    int kind;
+    f3 value;     // TERMINATE: radiance returned by this vertex (emission / 0); SPECULAR: attenuation;
+                  // DIFFUSE: weight = Attenuation * scatterPdf / pdfValue
+    f3 dir;       // next direction
+};
+
+template <uint32_t FEAT>
+__device__ __forceinline__ ShadeResult shade_vertex(const SceneView& sv, const RayD& ray, const Surface& s, const GrtMaterial& m,
+                                                    uint32_t pixel, uint32_t sample, uint32_t bounce, uint32_t k0, uint32_t k1, uint32_t* n_lightpdf) {
+    ShadeResult R;
+    R.dir = mk3(0, 0, 0);
+    if (m.type == GRT_MAT_DIFFUSE_LIGHT) {  // materials.go:142-155, camera.go:305-314
+        R.kind = SHADE_TERMINATE;
+        R.value = s.front ? texture_value<FEAT>(sv, m.tex, s.u, s.v, s.p) : mk3(0, 0, 0);
+        return R;
+    }
+    Rng rng;
+    rng.init(pixel, sample, bounce, GRT_STREAM_SHADE, k0, k1);
+    if ((FEAT & F_SPECULAR) && m.type == GRT_MAT_METAL) {  // materials.go:70-79
+        f3 refl = reflect(ray.d, s.n);
+        refl = unit(refl) + random_unit_vector(rng) * m.fuzz;
+        R.kind = SHADE_SPECULAR; R.value = mk3(m.albedo[0], m.albedo[1], m.albedo[2]); R.dir = refl;
+        return R;
+    }
+    if ((FEAT & F_SPECULAR) && m.type == GRT_MAT_DIELECTRIC) {  // materials.go:94-130
+        float ri = s.front ? 1.0f / m.ior : m.ior;
+        f3 ud = unit(ray.d);
+        float cosTheta = fminf(dot(-ud, s.n), 1.0f);
+        float sinTheta = sqrtf(1.0f - cosTheta * cosTheta);
+        bool cannotRefract = ri * sinTheta > 1.0f;
+        bool refl = cannotRefract;
+        if (!refl) {
+            float r0 = (1.0f - m.ior) / (1.0f + m.ior);
+            r0 *= r0;
+            float x = 1 - cosTheta, x2 = x * x;
+            float reflectance = r0 + (1 - r0) * (x2 * x2 * x);   // math.Pow(1-cos, 5)
+            refl = reflectance > rng.next();
+        }
+        R.kind = SHADE_SPECULAR; R.value = mk3(1, 1, 1);
+        R.dir = refl ? reflect(ud, s.n) : refract(ud, s.n, ri);
+        return R;
+    }
+    // Lambertian (CosinePdf) or Isotropic (SpherePdf): mixture with the light pdf
+    const bool iso = (FEAT & F_ISOTROPIC) && m.type == GRT_MAT_ISOTROPIC;
+    f3 att = texture_value<FEAT>(sv, m.tex, s.u, s.v, s.p);
+    const uint32_t nl = sv.ds->n_lights;
+    const GrtLight* lights = sv.lights();
+    d3 p64 = tod3(s.p);
+    f3 wn = unit(s.n);   // onb.W
+    f3 dir;
+    d3 dir64;
+    if (rng.next() < 0.5f) {  // pdf.go:69-74: p[0] = light
+        if (sv.ds->lights_mode == GRT_LIGHTS_LIST && nl == 0) {  // hittable.go:98-101: vec.Random()
+            float x = rng.next(), y = rng.next(), z = rng.next();
+            dir = mk3(x, y, z); dir64 = tod3(dir);
+        } else {
+            uint32_t li = 0;
+            if (sv.ds->lights_mode == GRT_LIGHTS_LIST) { li = (uint32_t)(rng.next() * (float)nl); if (li >= nl) li = nl - 1; }  // rand.Intn
+            float r1 = rng.next(), r2 = rng.next();
+            dir64 = light_random<FEAT>(lights + li, p64, r1, r2);
+            dir = tof3(dir64);
+        }
+    } else {
+        if (iso) dir = random_unit_vector(rng);                                   // pdf.go:21-23
+        else { float r1 = rng.next(), r2 = rng.next(); Onb b = make_onb(s.n); dir = onb_transform(b, random_cosine_direction(r1, r2)); }  // pdf.go:38-40
+        dir64 = tod3(dir);
+    }
+    // mixPdf.Value: 0.5 * lights.PdfValue + 0.5 * material pdf  (pdf.go:65-67, hittable.go:89-96)
+    double lp = 0.0;
+    if (nl > 0) {
+        double weight = 1.0 / (double)nl;
+        for (uint32_t i = 0; i < nl; i++) lp += weight * light_pdf<FEAT>(lights + i, p64, dir64);
+        if (n_lightpdf) *n_lightpdf += nl;
+    }
+    float mp, sp;
+    if (iso) { mp = 1.0f / (4 * GRT_PI_F); sp = mp; }
+    else {
+        float cosTheta = dot(unit(dir), wn);
+        mp = fmaxf(0.0f, cosTheta / GRT_PI_F);               // pdf.go:33-36
+        sp = cosTheta < 0 ? 0.0f : cosTheta / GRT_PI_F;      // materials.go:51-57
+    }
+    float pdfValue = 0.5f * (float)lp + 0.5f * mp;
+    if (pdfValue == 0.0f && sp == 0.0f) { R.kind = SHADE_NAN; R.value = mk3(0, 0, 0); return R; }  // 0 * x * (1/0) = NaN (camera.go:328)
+    R.kind = SHADE_DIFFUSE;
+    R.value = att * (sp / pdfValue);
+    R.dir = dir;
+    return R;
+}
+
+__device__ __forceinline__ f3 clamp_contribution(f3 c, float maxValue) {  // camera.go:334-341
+    float intensity = c.x + c.y + c.z;
+    if (intensity > maxValue) return c * (maxValue / intensity);
+    return c;
+}
+
+}  // namespace grtd

@@ -1,0 +1,371 @@
+// dev_trace.cuh — device scene view, primitive intersection and the stack-based
+// BVH traversal (closest hit) in the reference's child order.
+//
+// Reference: internal/hittable/bvh.go:69-82 (BVHNode.Hit), hittable.go:122-138
+// (HittableList.Hit), aabb/aabb.go:90-113 (slab test), objects.go:83-115
+// (sphere.Hit), :167-206 (quad.Hit, isInterior), :408-461 (Triangle.Hit),
+// medium.go:27-58 (constantMedium.Hit).
+#pragma once
+#include "dev_math.cuh"
+#include "../../include/grt.h"
+
+namespace grtd {
+
+// feature bits: kernels are compiled for feature supersets so that e.g. the
+// Cornell box never carries sphere / triangle / texture code.
+enum : uint32_t {
+    F_SPHERE = 1u << 0, F_QUAD = 1u << 1, F_TRI = 1u << 2, F_LIST = 1u << 3, F_MEDIUM = 1u << 4,
+    F_SPECULAR = 1u << 5, F_TEXTURE = 1u << 6, F_ISOTROPIC = 1u << 7, F_ROTQUAD = 1u << 8,
+    F_SPHERE_LIGHT = 1u << 9, F_QUAD_LIGHT = 1u << 10, F_TRI_LIGHT = 1u << 11, F_TRISHADE = 1u << 12,
+    F_DEFOCUS = 1u << 13, F_NODE = 1u << 14,
+    F_ALL = (1u << 15) - 1
+};
+#define GRT_NEEDS_F64(FEAT) (((FEAT) & (F_SPHERE | F_ROTQUAD)) != 0)
+
+// The small, hot arrays live in one blob (byte offsets below) so a block can
+// stage the whole thing in shared memory when it fits; large arrays stay in HBM.
+struct DevScene {
+    const unsigned char* blob;   // HBM copy of the blob
+    uint32_t blob_bytes;
+    uint32_t off_nodes, off_spheres, off_quads, off_items, off_media, off_materials, off_textures, off_lights, off_images;
+    uint32_t n_nodes, n_spheres, n_quads, n_items, n_media, n_materials, n_textures, n_lights, n_images;
+    const GrtTri* tris;          // HBM
+    const GrtTriShade* tri_shade;
+    const uint8_t* texels;
+    const GrtPerlin* perlins;
+    uint32_t n_tris, n_perlins;
+    uint32_t root, lights_mode, features, stack_need;
+};
+
+// View over either the shared-memory or the HBM copy of the blob.
+struct SceneView {
+    const unsigned char* base;
+    const DevScene* ds;
+    __device__ __forceinline__ const float4* nodes() const { return (const float4*)(base + ds->off_nodes); }
+    __device__ __forceinline__ const GrtSphere* spheres() const { return (const GrtSphere*)(base + ds->off_spheres); }
+    __device__ __forceinline__ const GrtQuad* quads() const { return (const GrtQuad*)(base + ds->off_quads); }
+    __device__ __forceinline__ const uint32_t* items() const { return (const uint32_t*)(base + ds->off_items); }
+    __device__ __forceinline__ const GrtMedium* media() const { return (const GrtMedium*)(base + ds->off_media); }
+    __device__ __forceinline__ const GrtMaterial* materials() const { return (const GrtMaterial*)(base + ds->off_materials); }
+    __device__ __forceinline__ const GrtTexture* textures() const { return (const GrtTexture*)(base + ds->off_textures); }
+    __device__ __forceinline__ const GrtLight* lights() const { return (const GrtLight*)(base + ds->off_lights); }
+    __device__ __forceinline__ const GrtImage* images() const { return (const GrtImage*)(base + ds->off_images); }
+};
+
+// Cooperative copy of the blob into shared memory (16-byte vectors).
+__device__ __forceinline__ void stage_blob(unsigned char* smem, const DevScene& ds) {
+    const uint4* src = (const uint4*)ds.blob;
+    uint4* dst = (uint4*)smem;
+    uint32_t n = ds.blob_bytes >> 4;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = __ldg(src + i);
+    __syncthreads();
+}
+
+struct RayD {
+    f3 o, d, invd;
+    float time;
+    // fp64 copies for the cancellation-prone sums (sphere quadratic, rotated-quad planes)
+    d3 o64, d64;
+    double a64;  // d.d
+};
+template <uint32_t FEAT>
+__device__ __forceinline__ void ray_setup(RayD& r, f3 o, f3 d, float time) {
+    r.o = o; r.d = d; r.time = time;
+    r.invd = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);  // aabb.go:96
+    if (GRT_NEEDS_F64(FEAT)) {
+        r.o64 = tod3(o); r.d64 = tod3(d);
+        r.a64 = dot(r.d64, r.d64);
+    }
+}
+
+struct HitInfo {
+    float t;
+    uint32_t ref;   // flat ref of the primitive / medium that was hit
+    float u, v;     // quad alpha/beta, triangle barycentrics (sphere: unused)
+};
+
+struct TraceCounters {
+    uint32_t box, sphere, quad, tri, medium;
+};
+
+// ---- slab test, aabb.go:90-113 -------------------------------------------
+// Same expression as the reference: t = (bound - origin) * (1/d), swap when
+// 1/d < 0, shrink, reject when max <= min.  fminf/fmaxf drop NaN where Go's
+// min/max propagate it; the difference only makes Go accept boxes that are
+// geometrically missed, never changes a closest hit.
+__device__ __forceinline__ bool box_hit(float4 n0, float4 n1, const RayD& r, float tmin, float tmax) {
+    // n0 = bmin.xyz, bmax.x ; n1 = bmax.yz, left, right
+    float t0x = (n0.x - r.o.x) * r.invd.x, t1x = (n0.w - r.o.x) * r.invd.x;
+    float t0y = (n0.y - r.o.y) * r.invd.y, t1y = (n1.x - r.o.y) * r.invd.y;
+    float t0z = (n0.z - r.o.z) * r.invd.z, t1z = (n1.y - r.o.z) * r.invd.z;
+    float ax = r.invd.x < 0 ? t1x : t0x, bx = r.invd.x < 0 ? t0x : t1x;
+    float ay = r.invd.y < 0 ? t1y : t0y, by = r.invd.y < 0 ? t0y : t1y;
+    float az = r.invd.z < 0 ? t1z : t0z, bz = r.invd.z < 0 ? t0z : t1z;
+    float lo = fmaxf(fmaxf(ax, ay), fmaxf(az, tmin));
+    float hi = fminf(fminf(bx, by), fminf(bz, tmax));
+    return !(hi <= lo);
+}
+
+// ---- sphere.Hit, objects.go:83-115 ----------------------------------------
+// The cancellation-prone sums (c = |oc|^2 - r^2, disc = h^2 - a c) are fp64;
+// the roots use the cancellation-free pair {c/q, q/a}, q = h + sign(h) sqrt(disc),
+// which equals {(h-s)/a, (h+s)/a} of the reference up to rounding.
+// `self`: the ray origin lies on this sphere; exact arithmetic has c == 0.
+__device__ __forceinline__ bool sphere_hit(const GrtSphere& s, const RayD& r, float tmin, float tmax, bool self, float& t_out) {
+    double cx = s.c0[0] + (double)r.time * (double)s.dc[0];
+    double cy = s.c0[1] + (double)r.time * (double)s.dc[1];
+    double cz = s.c0[2] + (double)r.time * (double)s.dc[2];
+    double ocx = cx - r.o64.x, ocy = cy - r.o64.y, ocz = cz - r.o64.z;
+    double h = r.d64.x * ocx + r.d64.y * ocy + r.d64.z * ocz;
+    double c = ocx * ocx + ocy * ocy + ocz * ocz - s.r * s.r;
+    if (self) c = 0.0;
+    double disc = h * h - r.a64 * c;
+    if (disc < 0) return false;
+    float hf = (float)h, af = (float)r.a64, cf = (float)c;
+    float sq = sqrtf((float)disc);
+    float nearr, farr;
+    if (hf >= 0) { float q = hf + sq; farr = q / af; nearr = cf / q; }
+    else { float q = hf - sq; nearr = q / af; farr = cf / q; }
+    float root = nearr;
+    if (!(tmin < root && root < tmax)) {   // Surrounds: open interval (objects.go:101-105)
+        root = farr;
+        if (!(tmin < root && root < tmax)) return false;
+    }
+    t_out = root;
+    return true;
+}
+
+// ---- quad.Hit + isInterior, objects.go:167-206 -----------------------------
+template <uint32_t FEAT>
+__device__ __forceinline__ bool quad_hit(const GrtQuad* q, const RayD& r, float tmin, float tmax, float& t_out, float& a_out, float& b_out) {
+    const float4 q0 = *(const float4*)&q->n[0];   // n, D
+    const float4 q1 = *(const float4*)&q->Q[0];   // Q, flags
+    float t;
+    if (!(FEAT & F_ROTQUAD) || (__float_as_uint(q1.w) & GRT_QUAD_AXIS_ALIGNED)) {
+        float denom = q0.x * r.d.x + q0.y * r.d.y + q0.z * r.d.z;
+        if (fabsf(denom) < 1e-8f) return false;
+        t = (q0.w - (q0.x * r.o.x + q0.y * r.o.y + q0.z * r.o.z)) / denom;
+    } else {
+        double denom = q->n64[0] * r.d64.x + q->n64[1] * r.d64.y + q->n64[2] * r.d64.z;
+        if (fabs(denom) < 1e-8) return false;
+        double num = q->D64 - (q->n64[0] * r.o64.x + q->n64[1] * r.o64.y + q->n64[2] * r.o64.z);
+        t = (float)num / (float)denom;
+    }
+    if (!(tmin <= t && t <= tmax)) return false;   // Contains: closed interval (objects.go:177)
+    const float4 q2 = *(const float4*)&q->A[0];
+    const float4 q3 = *(const float4*)&q->B[0];
+    float px = fmaf(t, r.d.x, r.o.x) - q1.x, py = fmaf(t, r.d.y, r.o.y) - q1.y, pz = fmaf(t, r.d.z, r.o.z) - q1.z;
+    float alpha = q2.x * px + q2.y * py + q2.z * pz;
+    float beta = q3.x * px + q3.y * py + q3.z * pz;
+    if (!(0.0f <= alpha && alpha <= 1.0f) || !(0.0f <= beta && beta <= 1.0f)) return false;  // objects.go:199
+    t_out = t; a_out = alpha; b_out = beta;
+    return true;
+}
+
+// ---- Triangle.Hit (Möller–Trumbore), objects.go:408-461 --------------------
+__device__ __forceinline__ bool tri_hit(const GrtTri* tp, const RayD& r, float tmin, float tmax, uint32_t self_id, float& t_out, float& u_out, float& v_out) {
+    const float4 a = __ldg((const float4*)tp);        // v0, mat
+    const float4 b = __ldg((const float4*)tp + 1);    // e0, id
+    const float4 c = __ldg((const float4*)tp + 2);    // e1, flags
+    if (__float_as_uint(b.w) == self_id) return false;
+    f3 e0 = mk3(b.x, b.y, b.z), e1 = mk3(c.x, c.y, c.z);
+    f3 pvec = cross(r.d, e1);
+    float det = dot(e0, pvec);
+    if (fabsf(det) < 1e-8f) return false;
+    float invDet = 1.0f / det;
+    f3 tvec = r.o - mk3(a.x, a.y, a.z);
+    float u = dot(tvec, pvec) * invDet;
+    if (u < 0 || u > 1) return false;
+    f3 qvec = cross(tvec, e0);
+    float v = dot(r.d, qvec) * invDet;
+    if (v < 0 || (u + v) > 1) return false;
+    float tl = dot(e1, qvec) * invDet;
+    if (tl < tmin || tl > tmax) return false;
+    t_out = tl; u_out = u; v_out = v;
+    return true;
+}
+
+#define GRT_STACK_MAIN 48
+#define GRT_STACK_BOUNDARY 32
+
+// Context for the medium's random draw (medium.go:47): stream (pixel, sample,
+// bounce, MEDIUM), draw index = running count of medium tests on this segment.
+struct MediumRngCtx {
+    uint32_t pixel, sample, bounce, k0, k1, count;
+};
+
+// Closest-hit traversal.  Visits children left first, right second
+// (bvh.go:73-79); the current closest t plays the role of rayT.Max.  List
+// items are visited in list order (hittable.go:129-136) through a
+// continuation entry so a long list never overflows the stack.
+template <uint32_t FEAT, bool BOUNDARY, bool STATS>
+__device__ bool closest_hit(const SceneView& sv, uint32_t root, const RayD& r, float tmin, float tmax,
+                                         uint32_t self_id, MediumRngCtx* mrng, HitInfo& hit, TraceCounters* tc) {
+    constexpr int STACK = BOUNDARY ? GRT_STACK_BOUNDARY : GRT_STACK_MAIN;
+    uint32_t stack[STACK];
+    int sp = 0;
+    stack[sp++] = root;
+    bool any = false;
+    const float4* nodes = sv.nodes();
+    while (sp > 0) {
+        uint32_t ref = stack[--sp];
+        uint32_t type = GRT_REF_TYPE(ref);
+        uint32_t idx = ref & GRT_REF_MASK;
+        if ((FEAT & F_LIST) && type == GRT_REF_LIST) {
+            // continuation: visit items()[idx], then the rest of the list
+            uint32_t item = sv.items()[idx];
+            if (!(item & GRT_LIST_LAST)) stack[sp++] = GRT_MAKE_REF(GRT_REF_LIST, idx + 1);
+            ref = item & ~GRT_LIST_LAST;
+            type = GRT_REF_TYPE(ref);
+            idx = ref & GRT_REF_MASK;
+            if (type == GRT_REF_LIST) { stack[sp++] = ref; continue; }  // nested list
+        }
+        if (type == GRT_REF_NODE) {
+            float4 n0 = nodes[2 * idx], n1 = nodes[2 * idx + 1];
+            if (STATS) tc->box++;
+            if (!box_hit(n0, n1, r, tmin, tmax)) continue;
+            uint32_t l = __float_as_uint(n1.z), rr = __float_as_uint(n1.w);
+            stack[sp++] = rr;
+            stack[sp++] = l;
+            continue;
+        }
+        if ((FEAT & F_QUAD) && type == GRT_REF_QUAD) {
+            const GrtQuad* q = sv.quads() + idx;
+            if (STATS) tc->quad++;
+            if (!BOUNDARY && q->id == self_id) continue;   // planar: an exact-arithmetic ray cannot re-hit it
+            float t, a, b;
+            if (quad_hit<FEAT>(q, r, tmin, tmax, t, a, b)) { any = true; tmax = t; hit.t = t; hit.ref = ref; hit.u = a; hit.v = b; }
+            continue;
+        }
+        if ((FEAT & F_SPHERE) && type == GRT_REF_SPHERE) {
+            const GrtSphere& s = sv.spheres()[idx];
+            if (STATS) tc->sphere++;
+            float t;
+            if (sphere_hit(s, r, tmin, tmax, !BOUNDARY && s.id == self_id, t)) { any = true; tmax = t; hit.t = t; hit.ref = ref; hit.u = 0; hit.v = 0; }
+            continue;
+        }
+        if ((FEAT & F_TRI) && type == GRT_REF_TRI) {
+            if (STATS) tc->tri++;
+            float t, u, v;
+            if (tri_hit(sv.ds->tris + idx, r, tmin, tmax, BOUNDARY ? GRT_NO_ID : self_id, t, u, v)) { any = true; tmax = t; hit.t = t; hit.ref = ref; hit.u = u; hit.v = v; }
+            continue;
+        }
+        if (!BOUNDARY && (FEAT & F_MEDIUM) && type == GRT_REF_MEDIUM) {
+            // constantMedium.Hit, medium.go:27-58
+            const GrtMedium m = sv.media()[idx];
+            if (STATS) tc->medium++;
+            HitInfo h1, h2;
+            const float INF = __int_as_float(0x7f800000);
+            if (!closest_hit<FEAT, true, STATS>(sv, m.boundary, r, -INF, INF, GRT_NO_ID, nullptr, h1, tc)) continue;
+            if (!closest_hit<FEAT, true, STATS>(sv, m.boundary, r, h1.t + 0.0001f, INF, GRT_NO_ID, nullptr, h2, tc)) continue;
+            float t1 = fmaxf(h1.t, tmin), t2 = fminf(h2.t, tmax);
+            if (t1 >= t2) continue;
+            t1 = fmaxf(0.0f, t1);
+            float rayLength = sqrtf(len2(r.d));
+            float inside = (t2 - t1) * rayLength;
+            // medium.go:47 draws only once both boundary hits exist and overlap the interval
+            float u = rng_draw(mrng->pixel, mrng->sample, mrng->bounce, GRT_STREAM_MEDIUM, mrng->count++, mrng->k0, mrng->k1);
+            float hitDistance = m.neg_inv_density * logf(u);
+            if (hitDistance > inside) continue;
+            float t = t1 + hitDistance / rayLength;
+            any = true; tmax = t; hit.t = t; hit.ref = ref; hit.u = 0; hit.v = 0;
+            continue;
+        }
+        // GRT_REF_NONE or a type compiled out: never hits
+    }
+    return any;
+}
+
+// ---- full hit record (HitRecord, hittable.go:14-34) ------------------------
+struct Surface {
+    f3 p, n;            // hit point, face-forwarded normal
+    float u, v;
+    uint32_t mat, id;
+    bool front;
+    bool is_surface;    // false for a medium scatter point
+    bool planar;
+};
+
+__device__ __forceinline__ void set_face_normal(Surface& s, f3 d, f3 outward) {  // hittable.go:27-34
+    s.front = dot(d, outward) < 0;
+    s.n = s.front ? outward : -outward;
+}
+
+// calculateSphereUV on the OBJECT-space outward normal (objects.go:44-50,113);
+// uvrot undoes the baked rotateY.
+__device__ __forceinline__ void sphere_uv(const GrtSphere& sp, Surface& s) {
+    f3 outward = s.front ? s.n : -s.n;
+    float c = sp.uvrot[0], sn = sp.uvrot[1];
+    f3 on = mk3(c * outward.x - sn * outward.z, outward.y, sn * outward.x + c * outward.z);
+    float theta = acosf(fminf(fmaxf(-on.y, -1.0f), 1.0f));
+    float phi = atan2f(-on.z, on.x) + GRT_PI_F;
+    s.u = phi / (2 * GRT_PI_F);
+    s.v = theta / GRT_PI_F;
+}
+
+template <uint32_t FEAT>
+__device__ __forceinline__ void finish_hit(const SceneView& sv, const RayD& r, const HitInfo& h, bool want_sphere_uv, Surface& s) {
+    uint32_t type = GRT_REF_TYPE(h.ref), idx = h.ref & GRT_REF_MASK;
+    s.p = mk3(fmaf(h.t, r.d.x, r.o.x), fmaf(h.t, r.d.y, r.o.y), fmaf(h.t, r.d.z, r.o.z));  // Ray.At, ray.go:35
+    s.u = h.u; s.v = h.v;
+    s.is_surface = true; s.planar = true;
+    if ((FEAT & F_QUAD) && type == GRT_REF_QUAD) {
+        const GrtQuad* q = sv.quads() + idx;
+        const float4 q0 = *(const float4*)&q->n[0];
+        s.mat = q->mat; s.id = q->id;
+        set_face_normal(s, r.d, mk3(q0.x, q0.y, q0.z));
+        return;
+    }
+    if ((FEAT & F_SPHERE) && type == GRT_REF_SPHERE) {
+        const GrtSphere& sp = sv.spheres()[idx];
+        s.mat = sp.mat; s.id = sp.id; s.planar = false;
+        // outward = (p - centre)/r with the hit point evaluated in fp64 (objects.go:109-111)
+        double cx = sp.c0[0] + (double)r.time * (double)sp.dc[0];
+        double cy = sp.c0[1] + (double)r.time * (double)sp.dc[1];
+        double cz = sp.c0[2] + (double)r.time * (double)sp.dc[2];
+        double t = (double)h.t;
+        double inv = 1.0 / sp.r;
+        f3 outward = mk3((float)((r.o64.x + t * r.d64.x - cx) * inv), (float)((r.o64.y + t * r.d64.y - cy) * inv), (float)((r.o64.z + t * r.d64.z - cz) * inv));
+        set_face_normal(s, r.d, outward);
+        if (want_sphere_uv) sphere_uv(sp, s);
+        return;
+    }
+    if ((FEAT & F_TRI) && type == GRT_REF_TRI) {
+        const GrtTri* tp = sv.ds->tris + idx;
+        const float4 a = __ldg((const float4*)tp), b = __ldg((const float4*)tp + 1), c = __ldg((const float4*)tp + 2);
+        s.mat = __float_as_uint(a.w); s.id = __float_as_uint(b.w);
+        uint32_t flags = __float_as_uint(c.w);
+        f3 nrm;
+        if ((FEAT & F_TRISHADE) && (flags & (GRT_TRI_HAS_NORMALS | GRT_TRI_HAS_UV))) {
+            const float4* sh = (const float4*)(sv.ds->tri_shade + idx);
+            float4 s0 = __ldg(sh), s1 = __ldg(sh + 1), s2 = __ldg(sh + 2), s3 = __ldg(sh + 3);
+            float w = 1.0f - h.u - h.v;
+            if (flags & GRT_TRI_HAS_UV) {  // objects.go:437-441
+                // uv = s2.y.. : n0(3) n1(3) n2(3) uv(6) -> floats 9..14
+                float uv0 = s2.y, uv1 = s2.z, uv2 = s2.w, uv3 = s3.x, uv4 = s3.y, uv5 = s3.z;
+                s.u = w * uv0 + h.u * uv2 + h.v * uv4;
+                s.v = w * uv1 + h.u * uv3 + h.v * uv5;
+            }
+            if (flags & GRT_TRI_HAS_NORMALS) {  // interpolateNormal, objects.go:389-405
+                f3 n0 = mk3(s0.x, s0.y, s0.z), n1 = mk3(s0.w, s1.x, s1.y), n2 = mk3(s1.z, s1.w, s2.x);
+                nrm = unit(mk3(w * n0.x + h.u * n1.x + h.v * n2.x, w * n0.y + h.u * n1.y + h.v * n2.y, w * n0.z + h.u * n1.z + h.v * n2.z));
+            } else {
+                nrm = unit(cross(mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z)));
+            }
+        } else {
+            nrm = unit(cross(mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z)));  // objects.go:268-270
+        }
+        set_face_normal(s, r.d, nrm);
+        return;
+    }
+    if ((FEAT & F_MEDIUM) && type == GRT_REF_MEDIUM) {  // medium.go:52-56
+        const GrtMedium m = sv.media()[idx];
+        s.mat = m.mat; s.id = m.id;
+        s.n = mk3(1, 0, 0); s.front = true; s.is_surface = false; s.planar = false;
+        s.u = 0; s.v = 0;   // the reference leaves u,v stale here
+        return;
+    }
+    s.mat = 0; s.id = GRT_NO_ID; s.n = mk3(0, 1, 0); s.front = true;
+}
+
+}  // namespace grtd

@@ -1,0 +1,20 @@
+// grt_internal.h — shared between the .cu translation units of libgrt_cuda.
+#pragma once
+#include <string>
+#include <cuda_runtime.h>
+#include "../../include/grt.h"
+
+#define GRT_MEGA_THREADS 128
+#define GRT_MEGA_MIN_BLOCKS 4
+// the scene blob is staged into shared memory when every resident block can hold a copy
+#define GRT_STAGE_MAX_BYTES (48u * 1024u)
+
+namespace grtd { struct DevScene; struct DevCamera; }
+
+void grt_set_error(const std::string& s);
+void grt_count_launch(uint64_t n);
+const grtd::DevScene* grt_internal_dev_scene(GrtSceneHandle h);
+int grt_internal_sm_count(GrtSceneHandle h);
+bool grt_internal_staged(GrtSceneHandle h);
+unsigned int* grt_internal_counter(GrtSceneHandle h);
+int grt_make_dev_camera(const GrtCamera* c, grtd::DevCamera* out);

@@ -1,0 +1,658 @@
+// grt_kernels.cu — sm_100a kernels and the C ABI of include/grt.h.
+//
+// Kernels:
+//   trace_batch_kernel   closest hit for a ray batch (parity checks 1 and 2)
+//   render_mega_kernel   persistent megakernel: camera ray -> loop { BVH
+//                        traversal, intersection, BSDF scatter, light/cosine
+//                        PDF mixture } -> recursive-clamp unwind -> per-pixel sum
+//   tonemap_kernel       color.go:14-46
+// The wavefront variant lives in grt_wavefront.cu.
+//
+// There is no CPU fallback anywhere in this file.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <atomic>
+#include <mutex>
+
+#include "dev_shade.cuh"
+#include "grt_internal.h"
+
+using namespace grtd;
+
+// ===========================================================================
+// error plumbing
+// ===========================================================================
+static thread_local std::string g_last_error;
+static std::atomic<uint64_t> g_launches(0);
+
+void grt_set_error(const std::string& s) { g_last_error = s; }
+void grt_count_launch(uint64_t n) { g_launches += n; }
+
+#define CUDA_TRY(call)                                                                          \
+    do {                                                                                        \
+        cudaError_t e_ = (call);                                                                \
+        if (e_ != cudaSuccess) {                                                                \
+            grt_set_error(std::string(#call) + ": " + cudaGetErrorString(e_));                  \
+            return GRT_E_CUDA;                                                                  \
+        }                                                                                       \
+    } while (0)
+
+// ===========================================================================
+// trace_batch: one thread per ray
+// ===========================================================================
+template <uint32_t FEAT, bool STAGED>
+__global__ void __launch_bounds__(128) trace_batch_kernel(const __grid_constant__ DevScene ds, const GrtRay* __restrict__ rays, uint64_t n, GrtHit* __restrict__ hits) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    SceneView sv;
+    sv.ds = &ds;
+    if (STAGED) { stage_blob(smem, ds); sv.base = smem; }
+    else sv.base = ds.blob;
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4* rp = (const float4*)(rays + i);
+    float4 a = __ldg(rp), b = __ldg(rp + 1), c = __ldg(rp + 2);
+    RayD r;
+    ray_setup<FEAT>(r, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), c.x);
+    uint32_t self_id = __float_as_uint(c.y);
+    MediumRngCtx mr;
+    mr.pixel = (uint32_t)i; mr.sample = (uint32_t)(i >> 32); mr.bounce = 0; mr.k0 = 0; mr.k1 = 0; mr.count = 0;
+    HitInfo h;
+    GrtHit out;
+    if (closest_hit<FEAT, false, false>(sv, ds.root, r, a.w, b.w, self_id, &mr, h, nullptr)) {
+        Surface s;
+        finish_hit<FEAT>(sv, r, h, true, s);
+        out.t = h.t; out.id = s.id; out.ref = h.ref; out.front_face = s.front ? 1u : 0u;
+        out.p[0] = s.p.x; out.p[1] = s.p.y; out.p[2] = s.p.z; out.u = s.u;
+        out.n[0] = s.n.x; out.n[1] = s.n.y; out.n[2] = s.n.z; out.v = s.v;
+    } else {
+        out.t = __int_as_float(0x7f800000); out.id = GRT_NO_ID; out.ref = GRT_MAKE_REF(GRT_REF_NONE, 0); out.front_face = 0;
+        out.p[0] = out.p[1] = out.p[2] = 0; out.u = 0; out.n[0] = out.n[1] = out.n[2] = 0; out.v = 0;
+    }
+    hits[i] = out;
+}
+
+// ===========================================================================
+// megakernel
+// ===========================================================================
+// One warp renders one pixel at a time.  Its 32 lanes pull strata from a
+// warp-uniform counter (ballot + popc ranks), so a lane whose path ends takes
+// the next sample immediately and the warp stays full until the pixel's
+// samples run out.  Lanes that find the current pixel exhausted start on the
+// warp's NEXT pixel (two pixels in flight), so there is no drain bubble even
+// with few samples per pixel (multi-GPU strata sharding).  Every decision is a
+// pure function of warp-internal state, so the fp32 sums are bit-reproducible.
+struct RenderParams {
+    DevScene scene;
+    DevCamera cam;
+    uint32_t k0, k1;
+    uint32_t sample_first, sample_stride, n_my;   // strata s = first + k*stride, k < n_my
+    int x0, y0, ww, wh;                            // pixel window
+    uint32_t n_pixels;                             // ww * wh
+    uint32_t claim;                                // pixels claimed per atomicAdd
+    float* rgb_sum;                                // device, W*H*3, += per pixel
+    unsigned int* counter;
+    GrtStats* stats;
+};
+
+#define WEIGHT_STACK 64
+
+template <uint32_t FEAT, bool STAGED, bool STATS>
+__global__ void __launch_bounds__(GRT_MEGA_THREADS, GRT_MEGA_MIN_BLOCKS) render_mega_kernel(const __grid_constant__ RenderParams P) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    SceneView sv;
+    sv.ds = &P.scene;
+    if (STAGED) { stage_blob(smem, P.scene); sv.base = smem; }
+    else sv.base = P.scene.blob;
+
+    const unsigned FULL = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const DevCamera& cam = P.cam;
+    const int max_depth = cam.max_depth;
+
+    // warp-uniform scheduling state
+    uint32_t blk_next = 0, blk_end = 0;      // unclaimed remainder of the warp's current pixel block
+    uint32_t pix_cur = 0xffffffffu;          // pixel being retired next (ordinal in the window)
+    uint32_t pix_nxt = 0xffffffffu;          // the pixel after it (claimed lazily)
+    uint32_t k_alloc = 0;                    // next stratum ordinal of the pixel being handed out
+    bool alloc_on_nxt = false;               // samples are being handed out from pix_nxt
+    bool exhausted = false;                  // no more pixels to claim
+
+    auto claim_pixel = [&]() -> uint32_t {
+        if (blk_next == blk_end && !exhausted) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(P.counter, P.claim);
+            base = __shfl_sync(FULL, base, 0);
+            if (base >= P.n_pixels) { exhausted = true; }
+            else { blk_next = base; blk_end = min(base + P.claim, P.n_pixels); }
+        }
+        if (blk_next < blk_end) return blk_next++;
+        return 0xffffffffu;
+    };
+    pix_cur = claim_pixel();
+    if (pix_cur == 0xffffffffu) return;
+
+    // lane state
+    bool active = false;
+    uint32_t my_parity = 0;                  // 0: my path belongs to pix_cur, 1: to pix_nxt
+    f3 acc0 = mk3(0, 0, 0), acc1 = mk3(0, 0, 0);
+    RayD ray;
+    uint32_t self_id = GRT_NO_ID, my_sample = 0, my_pixel_index = 0;
+    int bounce = 0;
+    f3 head = mk3(1, 1, 1), wtop = mk3(0, 0, 0);
+    int sp = 0;
+    f3 wstack[WEIGHT_STACK];
+    // stats
+    uint32_t st_paths = 0, st_segments = 0, st_diffuse = 0, st_specular = 0, st_lightpdf = 0, st_nan = 0;
+    TraceCounters tc;
+    tc.box = tc.sphere = tc.quad = tc.tri = tc.medium = 0;
+
+    for (;;) {
+        // ---- hand out strata to idle lanes ---------------------------------
+        unsigned need = __ballot_sync(FULL, !active);
+        while (need) {
+            uint32_t pix_alloc = alloc_on_nxt ? pix_nxt : pix_cur;
+            uint32_t avail = (pix_alloc == 0xffffffffu) ? 0u : (P.n_my - k_alloc);
+            uint32_t rank = __popc(need & lt_mask);
+            bool want = ((need >> lane) & 1u) != 0;
+            if (want && rank < avail) {
+                uint32_t k = k_alloc + rank;
+                my_sample = P.sample_first + k * P.sample_stride;
+                my_parity = alloc_on_nxt ? 1u : 0u;
+                int px = P.x0 + (int)(pix_alloc % (uint32_t)P.ww), py = P.y0 + (int)(pix_alloc / (uint32_t)P.ww);
+                my_pixel_index = (uint32_t)(py * cam.width + px);
+                f3 o, d; float time;
+                camera_ray<FEAT>(cam, px, py, my_sample, my_pixel_index, P.k0, P.k1, o, d, time);
+                ray_setup<FEAT>(ray, o, d, time);
+                self_id = GRT_NO_ID; bounce = 0; head = mk3(1, 1, 1); sp = 0;
+                active = true;
+                if (STATS) st_paths++;
+            }
+            uint32_t taken = min((uint32_t)__popc(need), avail);
+            k_alloc += taken;
+            need = __ballot_sync(FULL, !active);
+            if (!need) break;
+            // this pixel is used up: move allocation to the next pixel, at most one ahead
+            if (alloc_on_nxt) break;
+            if (pix_nxt == 0xffffffffu) pix_nxt = claim_pixel();
+            if (pix_nxt == 0xffffffffu) break;
+            alloc_on_nxt = true; k_alloc = 0;
+        }
+        // ---- retire pix_cur once no lane works on it and its strata are all handed out
+        bool cur_done_alloc = alloc_on_nxt || (k_alloc >= P.n_my);
+        unsigned on_cur = __ballot_sync(FULL, active && my_parity == 0u);
+        if (cur_done_alloc && on_cur == 0u) {
+            f3 s = acc0;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                s.x += __shfl_xor_sync(FULL, s.x, off);
+                s.y += __shfl_xor_sync(FULL, s.y, off);
+                s.z += __shfl_xor_sync(FULL, s.z, off);
+            }
+            if (lane == 0) {
+                int px = P.x0 + (int)(pix_cur % (uint32_t)P.ww), py = P.y0 + (int)(pix_cur / (uint32_t)P.ww);
+                float* dst = P.rgb_sum + ((size_t)py * cam.width + px) * 3;
+                dst[0] += s.x; dst[1] += s.y; dst[2] += s.z;   // this warp owns the pixel for the whole launch
+            }
+            acc0 = acc1; acc1 = mk3(0, 0, 0);
+            if (active) my_parity = 0u;   // survivors were on pix_nxt
+            if (alloc_on_nxt) { pix_cur = pix_nxt; pix_nxt = 0xffffffffu; alloc_on_nxt = false; }
+            else { pix_cur = claim_pixel(); k_alloc = 0; }
+            if (pix_cur == 0xffffffffu) break;
+            continue;
+        }
+        if (!active) continue;
+
+        // ---- one path segment: trace ------------------------------------------
+        if (STATS) st_segments++;
+        MediumRngCtx mr;
+        mr.pixel = my_pixel_index; mr.sample = my_sample; mr.bounce = (uint32_t)bounce; mr.k0 = P.k0; mr.k1 = P.k1; mr.count = 0;
+        HitInfo h;
+        const float INF = __int_as_float(0x7f800000);
+        bool hit = closest_hit<FEAT, false, STATS>(sv, P.scene.root, ray, 0.001f, INF, self_id, &mr, h, &tc);   // camera.go:300
+
+        f3 Lterm = mk3(0, 0, 0);
+        bool terminate = false, isnan_path = false;
+        if (!hit) { Lterm = cam.background; terminate = true; }   // camera.go:301
+        else {
+            Surface s;
+            finish_hit<FEAT>(sv, ray, h, false, s);
+            const GrtMaterial mat = sv.materials()[s.mat];
+            if ((FEAT & F_SPHERE) && (FEAT & F_TEXTURE) && GRT_REF_TYPE(h.ref) == GRT_REF_SPHERE && material_needs_uv<FEAT>(sv, mat))
+                sphere_uv(sv.spheres()[h.ref & GRT_REF_MASK], s);   // only image textures read a sphere's (u,v)
+            uint32_t nlp = 0;
+            ShadeResult R = shade_vertex<FEAT>(sv, ray, s, mat, my_pixel_index, my_sample, (uint32_t)bounce, P.k0, P.k1, STATS ? &nlp : nullptr);
+            if (STATS) st_lightpdf += nlp;
+            if (R.kind == SHADE_TERMINATE) { Lterm = R.value; terminate = true; }
+            else if (R.kind == SHADE_NAN) { isnan_path = true; terminate = true; }
+            else {
+                if (R.kind == SHADE_SPECULAR) {   // camera.go:315-317: unclamped, folds into the parent weight
+                    if (STATS) st_specular++;
+                    if (sp > 0) wtop = wtop * R.value; else head = head * R.value;
+                } else {                          // camera.go:319-330: a clamped vertex
+                    if (STATS) st_diffuse++;
+                    if (R.value.x == 0.0f && R.value.y == 0.0f && R.value.z == 0.0f) { terminate = true; }  // weight 0: the sample is 0 whatever follows
+                    else {
+                        if (sp > 0) wstack[sp - 1] = wtop;
+                        wtop = R.value; sp++;
+                    }
+                }
+                if (!terminate) {
+                    bounce++;
+                    if (bounce > max_depth) { terminate = true; }   // depth < 0 -> (0,0,0), camera.go:294-296
+                    else {
+                        ray_setup<FEAT>(ray, s.p, R.dir, ray.time);
+                        self_id = s.is_surface ? s.id : GRT_NO_ID;
+                    }
+                }
+            }
+        }
+        if (terminate) {
+            f3 L = Lterm;
+            if (isnan_path) { L = mk3(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000), __int_as_float(0x7fc00000)); if (STATS) st_nan++; }
+            else if (L.x != 0.0f || L.y != 0.0f || L.z != 0.0f) {
+                // unwind the recursion of camera.go:327-330 from the terminal radiance
+                if (sp > 0) {
+                    L = clamp_contribution(wtop * L, cam.max_contribution);
+                    for (int i = sp - 2; i >= 0; i--) L = clamp_contribution(wstack[i] * L, cam.max_contribution);
+                }
+                L = head * L;
+            }
+            if (my_parity == 0u) acc0 = acc0 + L; else acc1 = acc1 + L;
+            active = false;
+        }
+    }
+
+    if (STATS) {
+        unsigned long long v[11] = {st_paths, st_segments, tc.box, tc.sphere, tc.quad, tc.tri, tc.medium, st_diffuse, st_specular, st_lightpdf, st_nan};
+        unsigned long long* dst = (unsigned long long*)P.stats;
+#pragma unroll
+        for (int i = 0; i < 11; i++) {
+            unsigned long long x = v[i];
+            for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(FULL, x, off);
+            if (lane == 0 && x) atomicAdd(dst + i, x);
+        }
+    }
+}
+
+// ===========================================================================
+// tonemap, color.go:14-46
+// ===========================================================================
+__global__ void tonemap_kernel(const float* __restrict__ sum, uint8_t* __restrict__ out, uint64_t n, float scale) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float c = sum[i] * scale;          // pixelColor.Scale(pixelSamplesScale), camera.go:103
+    if (isnan(c)) c = 0.0f;            // color.go:28-36
+    c = c <= 0.0f ? 0.0f : sqrtf(c);   // linearToGamma :14-19
+    c = c < 0.0f ? 0.0f : (c > 0.99999f ? 0.99999f : c);   // intensity.Clamp :11,40-42
+    out[i] = (uint8_t)(int)(c * 256.0f);
+}
+
+// ===========================================================================
+// host side: upload, dispatch
+// ===========================================================================
+struct GrtSceneDev {
+    int device = 0;
+    DevScene ds;
+    void* d_blob = nullptr;
+    void* d_tris = nullptr;
+    void* d_tri_shade = nullptr;
+    void* d_texels = nullptr;
+    void* d_perlins = nullptr;
+    unsigned int* d_counter = nullptr;
+    bool staged = false;
+    int sm_count = 0;
+};
+
+static uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
+
+static uint32_t scan_features(const GrtScene* s) {
+    uint32_t f = 0;
+    if (s->n_nodes) f |= F_NODE;
+    if (s->n_spheres) f |= F_SPHERE;
+    if (s->n_quads) f |= F_QUAD;
+    if (s->n_tris) f |= F_TRI;
+    if (s->n_items) f |= F_LIST;
+    if (s->n_media) f |= F_MEDIUM;
+    for (uint32_t i = 0; i < s->n_materials; i++) {
+        uint32_t t = s->materials[i].type;
+        if (t == GRT_MAT_METAL || t == GRT_MAT_DIELECTRIC) f |= F_SPECULAR;
+        if (t == GRT_MAT_ISOTROPIC) f |= F_ISOTROPIC;
+    }
+    for (uint32_t i = 0; i < s->n_textures; i++) if (s->textures[i].type != GRT_TEX_SOLID) f |= F_TEXTURE;
+    for (uint32_t i = 0; i < s->n_quads; i++) if (!(s->quads[i].flags & GRT_QUAD_AXIS_ALIGNED)) f |= F_ROTQUAD;
+    for (uint32_t i = 0; i < s->n_lights; i++) {
+        if (s->lights[i].type == GRT_LIGHT_SPHERE) f |= F_SPHERE_LIGHT;
+        if (s->lights[i].type == GRT_LIGHT_QUAD) f |= F_QUAD_LIGHT;
+        if (s->lights[i].type == GRT_LIGHT_TRI) f |= F_TRI_LIGHT;
+    }
+    if (s->tri_shade) f |= F_TRISHADE;
+    return f;
+}
+
+static int validate_scene(const GrtScene* s) {
+    if (!s) { grt_set_error("scene is NULL"); return GRT_E_INVALID; }
+    if (s->abi_version != GRT_ABI_VERSION) { grt_set_error("GrtScene.abi_version mismatch"); return GRT_E_INVALID; }
+    auto check_ref = [&](uint32_t ref) -> bool {
+        uint32_t t = GRT_REF_TYPE(ref), i = ref & GRT_REF_MASK;
+        switch (t) {
+            case GRT_REF_NODE: return i < s->n_nodes;
+            case GRT_REF_SPHERE: return i < s->n_spheres;
+            case GRT_REF_QUAD: return i < s->n_quads;
+            case GRT_REF_TRI: return i < s->n_tris;
+            case GRT_REF_LIST: return i < s->n_items;
+            case GRT_REF_MEDIUM: return i < s->n_media;
+            case GRT_REF_NONE: return true;
+        }
+        return false;
+    };
+    if (!check_ref(s->root)) { grt_set_error("scene root ref out of range"); return GRT_E_INVALID; }
+    for (uint32_t i = 0; i < s->n_nodes; i++)
+        if (!check_ref(s->nodes[i].left) || !check_ref(s->nodes[i].right)) { grt_set_error("BVH node child ref out of range"); return GRT_E_INVALID; }
+    for (uint32_t i = 0; i < s->n_items; i++)
+        if (!check_ref(s->items[i] & ~GRT_LIST_LAST)) { grt_set_error("list item ref out of range"); return GRT_E_INVALID; }
+    if (s->n_items && !(s->items[s->n_items - 1] & GRT_LIST_LAST)) { grt_set_error("items[] does not end with GRT_LIST_LAST"); return GRT_E_INVALID; }
+    for (uint32_t i = 0; i < s->n_media; i++) {
+        if (!check_ref(s->media[i].boundary) || s->media[i].mat >= s->n_materials) { grt_set_error("medium ref out of range"); return GRT_E_INVALID; }
+    }
+    for (uint32_t i = 0; i < s->n_spheres; i++) if (s->spheres[i].mat >= s->n_materials) { grt_set_error("sphere material out of range"); return GRT_E_INVALID; }
+    for (uint32_t i = 0; i < s->n_quads; i++) if (s->quads[i].mat >= s->n_materials) { grt_set_error("quad material out of range"); return GRT_E_INVALID; }
+    for (uint32_t i = 0; i < s->n_tris; i++) if (s->tris[i].mat >= s->n_materials) { grt_set_error("triangle material out of range"); return GRT_E_INVALID; }
+    for (uint32_t i = 0; i < s->n_materials; i++) {
+        const GrtMaterial& m = s->materials[i];
+        if (m.type > GRT_MAT_ISOTROPIC) { grt_set_error("unknown material type"); return GRT_E_INVALID; }
+        if ((m.type == GRT_MAT_LAMBERTIAN || m.type == GRT_MAT_DIFFUSE_LIGHT || m.type == GRT_MAT_ISOTROPIC) && m.tex >= s->n_textures) { grt_set_error("material texture out of range"); return GRT_E_INVALID; }
+    }
+    for (uint32_t i = 0; i < s->n_textures; i++) {
+        const GrtTexture& t = s->textures[i];
+        if (t.type == GRT_TEX_CHECKER && (t.even >= s->n_textures || t.odd >= s->n_textures)) { grt_set_error("checker texture ids out of range"); return GRT_E_INVALID; }
+        if (t.type == GRT_TEX_IMAGE && t.aux >= s->n_images) { grt_set_error("image index out of range"); return GRT_E_INVALID; }
+        if (t.type == GRT_TEX_NOISE && (t.aux & 0xFFFFu) >= s->n_perlins) { grt_set_error("perlin index out of range"); return GRT_E_INVALID; }
+    }
+    if (s->max_depth_hint >= GRT_STACK_BOUNDARY) {
+        grt_set_error("scene needs a deeper traversal stack than the kernels provide");
+        return GRT_E_UNSUPPORTED;
+    }
+    return GRT_OK;
+}
+
+extern "C" int grt_abi_version(void) { return GRT_ABI_VERSION; }
+extern "C" const char* grt_last_error(void) { return g_last_error.c_str(); }
+extern "C" uint64_t grt_launch_count(void) { return g_launches.load(); }
+extern "C" int grt_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+static int need_device(int device) {
+    int n = grt_device_count();
+    if (n <= 0) { grt_set_error("no CUDA device available (libgrt_cuda has no CPU fallback)"); return GRT_E_NO_DEVICE; }
+    if (device < 0 || device >= n) { grt_set_error("CUDA device ordinal out of range"); return GRT_E_NO_DEVICE; }
+    return GRT_OK;
+}
+
+extern "C" int grt_scene_upload(const GrtScene* s, int device, GrtSceneHandle* out) {
+    if (!out) { grt_set_error("out handle is NULL"); return GRT_E_INVALID; }
+    *out = nullptr;
+    int rc = validate_scene(s);
+    if (rc) return rc;
+    rc = need_device(device);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(device));
+    GrtSceneDev* h = new GrtSceneDev();
+    h->device = device;
+    DevScene& ds = h->ds;
+    memset(&ds, 0, sizeof(ds));
+    // ---- pack the blob ------------------------------------------------------
+    uint32_t off = 0;
+    auto place = [&](uint32_t bytes) { uint32_t o = off; off = align16(off + bytes); return o; };
+    ds.off_nodes = place(s->n_nodes * (uint32_t)sizeof(GrtNode));
+    ds.off_spheres = place(s->n_spheres * (uint32_t)sizeof(GrtSphere));
+    ds.off_quads = place(s->n_quads * (uint32_t)sizeof(GrtQuad));
+    ds.off_items = place(s->n_items * 4u);
+    ds.off_media = place(s->n_media * (uint32_t)sizeof(GrtMedium));
+    ds.off_materials = place(s->n_materials * (uint32_t)sizeof(GrtMaterial));
+    ds.off_textures = place(s->n_textures * (uint32_t)sizeof(GrtTexture));
+    ds.off_lights = place(s->n_lights * (uint32_t)sizeof(GrtLight));
+    ds.off_images = place(s->n_images * (uint32_t)sizeof(GrtImage));
+    if (off == 0) off = 16;
+    std::vector<unsigned char> blob(off, 0);
+    auto put = [&](uint32_t o, const void* p, size_t bytes) { if (bytes) memcpy(blob.data() + o, p, bytes); };
+    put(ds.off_nodes, s->nodes, s->n_nodes * sizeof(GrtNode));
+    put(ds.off_spheres, s->spheres, s->n_spheres * sizeof(GrtSphere));
+    put(ds.off_quads, s->quads, s->n_quads * sizeof(GrtQuad));
+    put(ds.off_items, s->items, s->n_items * 4u);
+    put(ds.off_media, s->media, s->n_media * sizeof(GrtMedium));
+    put(ds.off_materials, s->materials, s->n_materials * sizeof(GrtMaterial));
+    put(ds.off_textures, s->textures, s->n_textures * sizeof(GrtTexture));
+    put(ds.off_lights, s->lights, s->n_lights * sizeof(GrtLight));
+    put(ds.off_images, s->images, s->n_images * sizeof(GrtImage));
+    ds.blob_bytes = off;
+    ds.n_nodes = s->n_nodes; ds.n_spheres = s->n_spheres; ds.n_quads = s->n_quads; ds.n_items = s->n_items; ds.n_media = s->n_media;
+    ds.n_materials = s->n_materials; ds.n_textures = s->n_textures; ds.n_lights = s->n_lights; ds.n_images = s->n_images;
+    ds.n_tris = s->n_tris; ds.n_perlins = s->n_perlins;
+    ds.root = s->root; ds.lights_mode = s->lights_mode; ds.stack_need = s->max_depth_hint;
+    ds.features = scan_features(s);
+    auto upload = [&](void** dptr, const void* src, size_t bytes) -> int {
+        *dptr = nullptr;
+        if (!bytes) return GRT_OK;
+        CUDA_TRY(cudaMalloc(dptr, bytes));
+        CUDA_TRY(cudaMemcpy(*dptr, src, bytes, cudaMemcpyHostToDevice));
+        return GRT_OK;
+    };
+    if ((rc = upload(&h->d_blob, blob.data(), blob.size()))) { grt_scene_free(h); return rc; }
+    if ((rc = upload(&h->d_tris, s->tris, (size_t)s->n_tris * sizeof(GrtTri)))) { grt_scene_free(h); return rc; }
+    if (s->tri_shade && (rc = upload(&h->d_tri_shade, s->tri_shade, (size_t)s->n_tris * sizeof(GrtTriShade)))) { grt_scene_free(h); return rc; }
+    if ((rc = upload(&h->d_texels, s->texels, (size_t)s->n_texel_bytes))) { grt_scene_free(h); return rc; }
+    if ((rc = upload(&h->d_perlins, s->perlins, (size_t)s->n_perlins * sizeof(GrtPerlin)))) { grt_scene_free(h); return rc; }
+    ds.blob = (const unsigned char*)h->d_blob;
+    ds.tris = (const GrtTri*)h->d_tris;
+    ds.tri_shade = (const GrtTriShade*)h->d_tri_shade;
+    ds.texels = (const uint8_t*)h->d_texels;
+    ds.perlins = (const GrtPerlin*)h->d_perlins;
+    CUDA_TRY(cudaMalloc((void**)&h->d_counter, 256));
+    h->staged = ds.blob_bytes <= GRT_STAGE_MAX_BYTES;
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    h->sm_count = prop.multiProcessorCount;
+    *out = h;
+    return GRT_OK;
+}
+
+extern "C" int grt_scene_free(GrtSceneHandle h) {
+    if (!h) return GRT_OK;
+    cudaSetDevice(h->device);
+    cudaFree(h->d_blob); cudaFree(h->d_tris); cudaFree(h->d_tri_shade); cudaFree(h->d_texels); cudaFree(h->d_perlins); cudaFree(h->d_counter);
+    delete h;
+    return GRT_OK;
+}
+
+const DevScene* grt_internal_dev_scene(GrtSceneHandle h) { return &h->ds; }
+int grt_internal_sm_count(GrtSceneHandle h) { return h->sm_count; }
+bool grt_internal_staged(GrtSceneHandle h) { return h->staged; }
+unsigned int* grt_internal_counter(GrtSceneHandle h) { return h->d_counter; }
+
+// ---- feature-variant dispatch ------------------------------------------------
+// Each variant is a feature SUPERSET compiled as its own kernel.
+#define V_CORNELL (F_NODE | F_QUAD | F_LIST | F_ROTQUAD | F_QUAD_LIGHT)
+#define V_SMOKE (V_CORNELL | F_MEDIUM | F_ISOTROPIC)
+#define V_SPHERES (F_NODE | F_SPHERE | F_LIST | F_SPECULAR | F_TEXTURE | F_SPHERE_LIGHT | F_DEFOCUS)
+#define V_MESH (F_NODE | F_SPHERE | F_TRI | F_LIST | F_SPECULAR | F_SPHERE_LIGHT | F_TRI_LIGHT | F_TRISHADE | F_DEFOCUS)
+#define V_FULL F_ALL
+
+template <uint32_t FEAT>
+static int launch_trace(GrtSceneDev* h, const GrtRay* d_rays, uint64_t n, GrtHit* d_hits, cudaStream_t st) {
+    unsigned blocks = (unsigned)((n + 127) / 128);
+    if (h->staged) {
+        CUDA_TRY(cudaFuncSetAttribute(trace_batch_kernel<FEAT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->ds.blob_bytes));
+        trace_batch_kernel<FEAT, true><<<blocks, 128, h->ds.blob_bytes, st>>>(h->ds, d_rays, n, d_hits);
+    } else {
+        trace_batch_kernel<FEAT, false><<<blocks, 128, 0, st>>>(h->ds, d_rays, n, d_hits);
+    }
+    grt_count_launch(1);
+    CUDA_TRY(cudaGetLastError());
+    return GRT_OK;
+}
+
+extern "C" int grt_trace_batch_device(GrtSceneHandle h, const GrtRay* d_rays, uint64_t n, GrtHit* d_hits, void* stream) {
+    if (!h || (!d_rays && n) || (!d_hits && n)) { grt_set_error("grt_trace_batch_device: NULL argument"); return GRT_E_INVALID; }
+    if (n == 0) return GRT_OK;
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    uint32_t f = h->ds.features;
+    if ((f & ~V_CORNELL) == 0) return launch_trace<V_CORNELL>(h, d_rays, n, d_hits, st);
+    if ((f & ~V_SMOKE) == 0) return launch_trace<V_SMOKE>(h, d_rays, n, d_hits, st);
+    if ((f & ~V_SPHERES) == 0) return launch_trace<V_SPHERES>(h, d_rays, n, d_hits, st);
+    if ((f & ~V_MESH) == 0) return launch_trace<V_MESH>(h, d_rays, n, d_hits, st);
+    return launch_trace<V_FULL>(h, d_rays, n, d_hits, st);
+}
+
+extern "C" int grt_trace_batch(GrtSceneHandle h, const GrtRay* rays, uint64_t n, GrtHit* hits) {
+    if (!h || (!rays && n) || (!hits && n)) { grt_set_error("grt_trace_batch: NULL argument"); return GRT_E_INVALID; }
+    if (n == 0) return GRT_OK;
+    CUDA_TRY(cudaSetDevice(h->device));
+    GrtRay* d_rays = nullptr; GrtHit* d_hits = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&d_rays, n * sizeof(GrtRay)));
+    cudaError_t e = cudaMalloc((void**)&d_hits, n * sizeof(GrtHit));
+    if (e != cudaSuccess) { cudaFree(d_rays); grt_set_error(cudaGetErrorString(e)); return GRT_E_CUDA; }
+    int rc = GRT_OK;
+    do {
+        if ((e = cudaMemcpy(d_rays, rays, n * sizeof(GrtRay), cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        rc = grt_trace_batch_device(h, d_rays, n, d_hits, nullptr);
+        if (rc) break;
+        if ((e = cudaDeviceSynchronize()) != cudaSuccess) break;
+        if ((e = cudaMemcpy(hits, d_hits, n * sizeof(GrtHit), cudaMemcpyDeviceToHost)) != cudaSuccess) break;
+    } while (0);
+    cudaFree(d_rays); cudaFree(d_hits);
+    if (e != cudaSuccess) { grt_set_error(cudaGetErrorString(e)); return GRT_E_CUDA; }
+    return rc;
+}
+
+int grt_make_dev_camera(const GrtCamera* c, DevCamera* out) {
+    if (!c) { grt_set_error("camera is NULL"); return GRT_E_INVALID; }
+    if (c->width <= 0 || c->height <= 0 || c->spp_sqrt <= 0 || c->max_depth < 0) { grt_set_error("camera: width/height/spp_sqrt must be positive"); return GRT_E_INVALID; }
+    if (c->max_depth + 1 > WEIGHT_STACK) { grt_set_error("camera: MaxDepth exceeds the kernel's weight stack (63)"); return GRT_E_UNSUPPORTED; }
+    if ((uint64_t)c->spp_sqrt * (uint64_t)c->spp_sqrt > 0xffffffffull) { grt_set_error("camera: more than 2^32 strata per pixel"); return GRT_E_UNSUPPORTED; }
+    DevCamera d;
+    auto f = [](const double* v) { return f3{(float)v[0], (float)v[1], (float)v[2]}; };
+    d.center = f(c->center);
+    double rel[3] = {c->pixel00[0] - c->center[0], c->pixel00[1] - c->center[1], c->pixel00[2] - c->center[2]};
+    d.p00_rel = f(rel);
+    d.du = f(c->delta_u); d.dv = f(c->delta_v); d.defu = f(c->defocus_u); d.defv = f(c->defocus_v);
+    d.background = f(c->background);
+    d.max_contribution = (float)c->max_contribution;
+    d.recip_spp_sqrt = (float)(1.0 / (double)c->spp_sqrt);
+    d.defocus_angle = (float)c->defocus_angle;
+    d.width = c->width; d.height = c->height; d.spp_sqrt = c->spp_sqrt; d.max_depth = c->max_depth;
+    *out = d;
+    return GRT_OK;
+}
+
+template <uint32_t FEAT>
+static int launch_mega(GrtSceneDev* h, RenderParams& P, bool stats, cudaStream_t st) {
+    int blocks = h->sm_count * GRT_MEGA_MIN_BLOCKS;
+    size_t smem = h->staged ? h->ds.blob_bytes : 0;
+#define GRT_LAUNCH(STAGED_, STATS_)                                                                                           \
+    do {                                                                                                                      \
+        if (smem) CUDA_TRY(cudaFuncSetAttribute(render_mega_kernel<FEAT, STAGED_, STATS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        render_mega_kernel<FEAT, STAGED_, STATS_><<<blocks, GRT_MEGA_THREADS, smem, st>>>(P);                                 \
+    } while (0)
+    if (h->staged) { if (stats) GRT_LAUNCH(true, true); else GRT_LAUNCH(true, false); }
+    else { if (stats) GRT_LAUNCH(false, true); else GRT_LAUNCH(false, false); }
+#undef GRT_LAUNCH
+    grt_count_launch(1);
+    CUDA_TRY(cudaGetLastError());
+    return GRT_OK;
+}
+
+int grt_render_wavefront(GrtSceneHandle h, const GrtCamera* cam, const GrtOptions* opt, float* d_rgb_sum, cudaStream_t st, GrtStats* d_stats);
+
+extern "C" int grt_render_device(GrtSceneHandle h, const GrtCamera* cam, const GrtOptions* opt, float* d_rgb_sum, void* stream, GrtStats* d_stats) {
+    if (!h || !cam || !opt || !d_rgb_sum) { grt_set_error("grt_render_device: NULL argument"); return GRT_E_INVALID; }
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (opt->variant == GRT_VARIANT_WAVEFRONT) return grt_render_wavefront(h, cam, opt, d_rgb_sum, st, d_stats);
+    if (opt->variant != GRT_VARIANT_MEGAKERNEL) { grt_set_error("unknown GrtOptions.variant"); return GRT_E_INVALID; }
+    RenderParams P;
+    memset(&P, 0, sizeof(P));
+    int rc = grt_make_dev_camera(cam, &P.cam);
+    if (rc) return rc;
+    P.scene = h->ds;
+    P.k0 = (uint32_t)opt->seed; P.k1 = (uint32_t)(opt->seed >> 32);
+    uint32_t S2 = (uint32_t)cam->spp_sqrt * (uint32_t)cam->spp_sqrt;
+    uint32_t stride = opt->sample_stride ? opt->sample_stride : 1u;
+    if (opt->sample_first >= S2) return GRT_OK;   // nothing to do for this shard
+    P.sample_first = opt->sample_first; P.sample_stride = stride;
+    P.n_my = (S2 - opt->sample_first + stride - 1) / stride;
+    int x0 = opt->x0, y0 = opt->y0, x1 = opt->x1, y1 = opt->y1;
+    if (x0 == 0 && y0 == 0 && x1 == 0 && y1 == 0) { x1 = cam->width; y1 = cam->height; }
+    if (x0 < 0 || y0 < 0 || x1 > cam->width || y1 > cam->height || x1 <= x0 || y1 <= y0) { grt_set_error("GrtOptions pixel window out of range"); return GRT_E_INVALID; }
+    P.x0 = x0; P.y0 = y0; P.ww = x1 - x0; P.wh = y1 - y0;
+    P.n_pixels = (uint32_t)P.ww * (uint32_t)P.wh;
+    // pixels per claim: enough work per atomic, small enough for a short tail
+    uint64_t paths_per_pixel = P.n_my;
+    uint32_t claim = (uint32_t)(8192 / (paths_per_pixel ? paths_per_pixel : 1));
+    if (claim < 1) claim = 1;
+    if (claim > 64) claim = 64;
+    P.claim = claim;
+    P.rgb_sum = d_rgb_sum;
+    P.counter = h->d_counter;
+    P.stats = d_stats;
+    CUDA_TRY(cudaMemsetAsync(h->d_counter, 0, 4, st));
+    bool stats = (opt->flags & GRT_OPT_STATS) && d_stats;
+    uint32_t f = h->ds.features | (cam->defocus_angle > 0 ? F_DEFOCUS : 0u);
+    if ((f & ~V_CORNELL) == 0) return launch_mega<V_CORNELL>(h, P, stats, st);
+    if ((f & ~V_SMOKE) == 0) return launch_mega<V_SMOKE>(h, P, stats, st);
+    if ((f & ~V_SPHERES) == 0) return launch_mega<V_SPHERES>(h, P, stats, st);
+    if ((f & ~V_MESH) == 0) return launch_mega<V_MESH>(h, P, stats, st);
+    return launch_mega<V_FULL>(h, P, stats, st);
+}
+
+extern "C" int grt_tonemap_device(const float* d_rgb_sum, uint8_t* d_rgb8, uint64_t n_values, float scale, void* stream) {
+    if (!d_rgb_sum || !d_rgb8) { grt_set_error("grt_tonemap_device: NULL argument"); return GRT_E_INVALID; }
+    if (!n_values) return GRT_OK;
+    tonemap_kernel<<<(unsigned)((n_values + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_rgb_sum, d_rgb8, n_values, scale);
+    grt_count_launch(1);
+    CUDA_TRY(cudaGetLastError());
+    return GRT_OK;
+}
+
+extern "C" int grt_render(GrtSceneHandle h, const GrtCamera* cam, const GrtOptions* opt, float* rgb_sum, uint8_t* rgb8, GrtStats* stats) {
+    if (!h || !cam || !opt || !rgb_sum) { grt_set_error("grt_render: NULL argument"); return GRT_E_INVALID; }
+    if (cam->width <= 0 || cam->height <= 0) { grt_set_error("camera: width/height must be positive"); return GRT_E_INVALID; }
+    CUDA_TRY(cudaSetDevice(h->device));
+    size_t nval = (size_t)cam->width * cam->height * 3;
+    float* d_sum = nullptr; uint8_t* d_rgb8 = nullptr; GrtStats* d_stats = nullptr;
+    int rc = GRT_OK;
+    cudaError_t e = cudaSuccess;
+    do {
+        if ((e = cudaMalloc((void**)&d_sum, nval * sizeof(float))) != cudaSuccess) break;
+        if ((e = cudaMemcpy(d_sum, rgb_sum, nval * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        if (stats) {
+            if ((e = cudaMalloc((void**)&d_stats, sizeof(GrtStats))) != cudaSuccess) break;
+            if ((e = cudaMemset(d_stats, 0, sizeof(GrtStats))) != cudaSuccess) break;
+        }
+        GrtOptions o = *opt;
+        if (stats) o.flags |= GRT_OPT_STATS;
+        rc = grt_render_device(h, cam, &o, d_sum, nullptr, d_stats);
+        if (rc) break;
+        if (rgb8) {
+            if ((e = cudaMalloc((void**)&d_rgb8, nval)) != cudaSuccess) break;
+            float scale = 1.0f / (float)((double)cam->spp_sqrt * (double)cam->spp_sqrt);
+            rc = grt_tonemap_device(d_sum, d_rgb8, nval, scale, nullptr);
+            if (rc) break;
+        }
+        if ((e = cudaDeviceSynchronize()) != cudaSuccess) break;
+        if ((e = cudaMemcpy(rgb_sum, d_sum, nval * sizeof(float), cudaMemcpyDeviceToHost)) != cudaSuccess) break;
+        if (rgb8 && (e = cudaMemcpy(rgb8, d_rgb8, nval, cudaMemcpyDeviceToHost)) != cudaSuccess) break;
+        if (stats && (e = cudaMemcpy(stats, d_stats, sizeof(GrtStats), cudaMemcpyDeviceToHost)) != cudaSuccess) break;
+    } while (0);
+    cudaFree(d_sum); cudaFree(d_rgb8); cudaFree(d_stats);
+    if (e != cudaSuccess) { grt_set_error(std::string("grt_render: ") + cudaGetErrorString(e)); return GRT_E_CUDA; }
+    return rc;
+}

@@ -1,0 +1,146 @@
+// grt_multi.cu — in-process multi-GPU render (the `-gpus N` path of the CLI and
+// of a cgo caller, which is ONE process).  Each device holds a scene replica
+// and renders the strata s ≡ g (mod N) into a private fp32 sum buffer; the
+// buffers are combined with ONE ncclReduce(sum, root = devices[0]) over
+// NVLink/NVSwitch before tonemap.  (bench.py instead runs one process per GPU
+// and reduces through torch.distributed's NCCL communicator.)
+//
+// NCCL is bound at run time with dlopen so that libgrt_cuda has no link-time
+// dependency on a particular libnccl (PyTorch bundles its own).
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "grt_internal.h"
+
+namespace {
+typedef struct ncclComm* ncclComm_t;
+typedef int ncclResult_t;
+enum { ncclFloat32 = 7, ncclSum = 0 };
+struct Nccl {
+    void* lib = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Reduce)(const void*, void*, size_t, int, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool load() {
+        if (lib) return true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so", nullptr};
+        for (int i = 0; names[i] && !lib; i++) lib = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) return false;
+        CommInitAll = (decltype(CommInitAll))dlsym(lib, "ncclCommInitAll");
+        CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+        GroupStart = (decltype(GroupStart))dlsym(lib, "ncclGroupStart");
+        GroupEnd = (decltype(GroupEnd))dlsym(lib, "ncclGroupEnd");
+        Reduce = (decltype(Reduce))dlsym(lib, "ncclReduce");
+        GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+        return CommInitAll && CommDestroy && GroupStart && GroupEnd && Reduce;
+    }
+};
+Nccl g_nccl;
+}  // namespace
+
+#define CU(call)                                                                                 \
+    do {                                                                                         \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess) { grt_set_error(std::string(#call) + ": " + cudaGetErrorString(e_)); rc = GRT_E_CUDA; goto done; } \
+    } while (0)
+#define NC(call)                                                                                 \
+    do {                                                                                         \
+        ncclResult_t r_ = (call);                                                                \
+        if (r_ != 0) { grt_set_error(std::string(#call) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "nccl error")); rc = GRT_E_NCCL; goto done; } \
+    } while (0)
+
+extern "C" int grt_render_multi(const GrtScene* scene, const GrtCamera* cam, const GrtOptions* opt, const int* devices, int n,
+                                float* rgb_sum, uint8_t* rgb8, double* kernel_ms) {
+    if (!scene || !cam || !opt || !devices || n < 1 || !rgb_sum) { grt_set_error("grt_render_multi: bad argument"); return GRT_E_INVALID; }
+    int have = grt_device_count();
+    if (have <= 0) { grt_set_error("no CUDA device available (libgrt_cuda has no CPU fallback)"); return GRT_E_NO_DEVICE; }
+    for (int i = 0; i < n; i++) if (devices[i] < 0 || devices[i] >= have) { grt_set_error("device ordinal out of range"); return GRT_E_NO_DEVICE; }
+    if (n > 1 && !g_nccl.load()) { grt_set_error("libnccl.so.2 could not be loaded"); return GRT_E_NCCL; }
+
+    int rc = GRT_OK;
+    size_t nval = (size_t)cam->width * cam->height * 3;
+    std::vector<GrtSceneHandle> hs(n, nullptr);
+    std::vector<float*> d_sum(n, nullptr);
+    std::vector<cudaStream_t> st(n, nullptr);
+    std::vector<cudaEvent_t> e0(n, nullptr), e1(n, nullptr);
+    std::vector<ncclComm_t> comms(n, nullptr);
+    uint8_t* d_rgb8 = nullptr;
+    bool comms_ok = false;
+
+    for (int g = 0; g < n; g++) {
+        rc = grt_scene_upload(scene, devices[g], &hs[g]);
+        if (rc) goto done;
+        CU(cudaSetDevice(devices[g]));
+        CU(cudaStreamCreateWithFlags(&st[g], cudaStreamNonBlocking));
+        CU(cudaEventCreate(&e0[g]));
+        CU(cudaEventCreate(&e1[g]));
+        CU(cudaMalloc((void**)&d_sum[g], nval * sizeof(float)));
+        if (g == 0) CU(cudaMemcpyAsync(d_sum[g], rgb_sum, nval * sizeof(float), cudaMemcpyHostToDevice, st[g]));
+        else CU(cudaMemsetAsync(d_sum[g], 0, nval * sizeof(float), st[g]));
+    }
+    if (n > 1) { NC(g_nccl.CommInitAll(comms.data(), n, devices)); comms_ok = true; }
+
+    // every device renders its strata shard, concurrently
+    for (int g = 0; g < n; g++) {
+        GrtOptions o = *opt;
+        uint32_t base_stride = opt->sample_stride ? opt->sample_stride : 1u;
+        o.sample_first = opt->sample_first + (uint32_t)g * base_stride;
+        o.sample_stride = base_stride * (uint32_t)n;
+        o.device = devices[g];
+        CU(cudaSetDevice(devices[g]));
+        CU(cudaEventRecord(e0[g], st[g]));
+        rc = grt_render_device(hs[g], cam, &o, d_sum[g], st[g], nullptr);
+        if (rc) goto done;
+    }
+    if (n > 1) {
+        NC(g_nccl.GroupStart());
+        for (int g = 0; g < n; g++) {
+            ncclResult_t r_ = g_nccl.Reduce(d_sum[g], d_sum[g], nval, ncclFloat32, ncclSum, 0, comms[g], st[g]);
+            if (r_ != 0) { g_nccl.GroupEnd(); grt_set_error("ncclReduce failed"); rc = GRT_E_NCCL; goto done; }
+        }
+        NC(g_nccl.GroupEnd());
+    }
+    for (int g = 0; g < n; g++) {
+        CU(cudaSetDevice(devices[g]));
+        CU(cudaEventRecord(e1[g], st[g]));
+    }
+    CU(cudaSetDevice(devices[0]));
+    if (rgb8) {
+        CU(cudaMalloc((void**)&d_rgb8, nval));
+        float scale = 1.0f / (float)((double)cam->spp_sqrt * (double)cam->spp_sqrt);
+        rc = grt_tonemap_device(d_sum[0], d_rgb8, nval, scale, st[0]);
+        if (rc) goto done;
+    }
+    {
+        double worst = 0;
+        for (int g = 0; g < n; g++) {
+            CU(cudaSetDevice(devices[g]));
+            CU(cudaStreamSynchronize(st[g]));
+            float ms = 0;
+            CU(cudaEventElapsedTime(&ms, e0[g], e1[g]));
+            if (ms > worst) worst = ms;
+        }
+        if (kernel_ms) *kernel_ms = worst;
+    }
+    CU(cudaSetDevice(devices[0]));
+    CU(cudaMemcpy(rgb_sum, d_sum[0], nval * sizeof(float), cudaMemcpyDeviceToHost));
+    if (rgb8) CU(cudaMemcpy(rgb8, d_rgb8, nval, cudaMemcpyDeviceToHost));
+
+done:
+    for (int g = 0; g < n; g++) {
+        if (hs[g]) cudaSetDevice(devices[g]);
+        if (comms_ok && comms[g]) g_nccl.CommDestroy(comms[g]);
+        if (d_sum[g]) cudaFree(d_sum[g]);
+        if (e0[g]) cudaEventDestroy(e0[g]);
+        if (e1[g]) cudaEventDestroy(e1[g]);
+        if (st[g]) cudaStreamDestroy(st[g]);
+        if (hs[g]) grt_scene_free(hs[g]);
+    }
+    if (d_rgb8) { cudaSetDevice(devices[0]); cudaFree(d_rgb8); }
+    return rc;
+}

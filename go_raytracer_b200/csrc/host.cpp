@@ -1,0 +1,190 @@
+// host.cpp — C API over the host-side mirror (include/grt_host.h).
+#include "../../include/grt_host.h"
+#include "scene_ir.hpp"
+#include "scenes.hpp"
+#include "flatten.hpp"
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <memory>
+
+using grt::ir::V3;
+
+static thread_local std::string g_host_error;
+static int fail(const std::string& e) { g_host_error = e; return -1; }
+
+struct GrtHostScene {
+    grt::ir::Scene ir;
+    std::unique_ptr<grt::flat::FlatScene> flat;
+};
+
+static V3 v3(const double* p) { return V3(p[0], p[1], p[2]); }
+
+#define GUARD(expr)                                   \
+    try { return (expr); }                            \
+    catch (const std::exception& ex) { return fail(ex.what()); }
+
+extern "C" {
+
+const char* grt_host_last_error(void) { return g_host_error.c_str(); }
+GrtHostScene* grt_host_scene_new(void) { return new GrtHostScene(); }
+void grt_host_scene_free(GrtHostScene* s) { delete s; }
+
+int grt_host_solid_color(GrtHostScene* s, double r, double g, double b) { GUARD(s->ir.NewSolidColor(V3(r, g, b))); }
+int grt_host_checkerboard(GrtHostScene* s, double scale, int even_tex, int odd_tex) {
+    if (even_tex < 0 || odd_tex < 0 || even_tex >= (int)s->ir.textures.size() || odd_tex >= (int)s->ir.textures.size()) return fail("bad texture id");
+    GUARD(s->ir.NewCheckerboard(scale, even_tex, odd_tex));
+}
+int grt_host_image(GrtHostScene* s, int w, int h, const uint8_t* rgb) {
+    if (w <= 0 || h <= 0 || !rgb) return fail("bad image");
+    GUARD(s->ir.AddImage(w, h, rgb));
+}
+int grt_host_image_texture(GrtHostScene* s, int image) {
+    if (image < 0 || image >= (int)s->ir.images.size()) return fail("bad image id");
+    GUARD(s->ir.NewImageTexture(image));
+}
+int grt_host_noise_texture(GrtHostScene* s, double scale, int variant, uint64_t seed) {
+    if (variant < 1 || variant > 3) return fail("bad noise variant");
+    GUARD(s->ir.NewNoiseTextureWithType(scale, variant, seed));
+}
+static bool okTex(GrtHostScene* s, int t) { return t >= 0 && t < (int)s->ir.textures.size(); }
+int grt_host_lambertian(GrtHostScene* s, int tex) { if (!okTex(s, tex)) return fail("bad texture id"); GUARD(s->ir.NewTexturedLambertian(tex)); }
+int grt_host_metal(GrtHostScene* s, double r, double g, double b, double fuzz) { GUARD(s->ir.NewMetal(V3(r, g, b), fuzz)); }
+int grt_host_dielectric(GrtHostScene* s, double ior) { GUARD(s->ir.NewDielectric(ior)); }
+int grt_host_diffuse_light(GrtHostScene* s, int tex) { if (!okTex(s, tex)) return fail("bad texture id"); GUARD(s->ir.NewDiffuseLightTextured(tex)); }
+int grt_host_isotropic(GrtHostScene* s, int tex) { if (!okTex(s, tex)) return fail("bad texture id"); GUARD(s->ir.NewIsotropicTexture(tex)); }
+
+int grt_host_sphere(GrtHostScene* s, const double c[3], double r, int mat) { GUARD(s->ir.NewSphere(v3(c), r, mat)); }
+int grt_host_motion_sphere(GrtHostScene* s, const double c1[3], const double c2[3], double r, int mat) { GUARD(s->ir.NewMotionSphere(v3(c1), v3(c2), r, mat)); }
+int grt_host_quad(GrtHostScene* s, const double Q[3], const double u[3], const double v[3], int mat) { GUARD(s->ir.NewQuad(v3(Q), v3(u), v3(v), mat)); }
+int grt_host_box(GrtHostScene* s, const double a[3], const double b[3], int mat) { GUARD(s->ir.NewBox(v3(a), v3(b), mat)); }
+int grt_host_triangle(GrtHostScene* s, const double v[9], const double* n9, const double* uv6, int mat) {
+    V3 vv[3] = {v3(v), v3(v + 3), v3(v + 6)};
+    V3 nn[3];
+    double uv[3][2];
+    if (n9) for (int i = 0; i < 3; i++) nn[i] = v3(n9 + 3 * i);
+    if (uv6) for (int i = 0; i < 3; i++) { uv[i][0] = uv6[2 * i]; uv[i][1] = uv6[2 * i + 1]; }
+    GUARD(s->ir.NewTriangleFull(vv, n9 ? nn : nullptr, uv6 ? uv : nullptr, mat));
+}
+int grt_host_list(GrtHostScene* s) { GUARD(s->ir.NewHittableList()); }
+int grt_host_list_add(GrtHostScene* s, int list, int obj) {
+    try { s->ir.Add(list, obj); return 0; } catch (const std::exception& ex) { return fail(ex.what()); }
+}
+int grt_host_bvh(GrtHostScene* s, int list) { GUARD(s->ir.BuildBVH(list)); }
+int grt_host_translate(GrtHostScene* s, int obj, const double off[3]) { GUARD(s->ir.Translate(obj, v3(off))); }
+int grt_host_rotate_y(GrtHostScene* s, int obj, double degrees) { GUARD(s->ir.RotateY(obj, degrees)); }
+int grt_host_constant_medium(GrtHostScene* s, int boundary, double density, int tex) {
+    if (!okTex(s, tex)) return fail("bad texture id");
+    GUARD(s->ir.ConstantMediumTexture(boundary, density, tex));
+}
+int grt_host_set_world(GrtHostScene* s, int obj) { try { s->ir.checkH(obj); s->ir.world = obj; return 0; } catch (const std::exception& ex) { return fail(ex.what()); } }
+int grt_host_set_lights(GrtHostScene* s, int obj) { try { s->ir.checkH(obj); s->ir.lights = obj; return 0; } catch (const std::exception& ex) { return fail(ex.what()); } }
+
+static void toC(const grt::ir::CameraConfig& c, GrtCameraConfig* o) {
+    o->AspectRatio = c.AspectRatio; o->Width = c.Width; o->SamplesPerPixel = c.SamplesPerPixel; o->MaxDepth = c.MaxDepth; o->MaxThreads = c.MaxThreads;
+    o->VerticalFOV = c.VerticalFOV; o->DefocusAngle = c.DefocusAngle; o->FocusDistance = c.FocusDistance;
+    o->Background[0] = c.Background.x; o->Background[1] = c.Background.y; o->Background[2] = c.Background.z;
+    o->MaxContribution = c.MaxContribution;
+    const V3* src[3] = {&c.lookFrom, &c.lookAt, &c.vup};
+    double* dst[3] = {o->lookFrom, o->lookAt, o->vup};
+    for (int i = 0; i < 3; i++) { dst[i][0] = src[i]->x; dst[i][1] = src[i]->y; dst[i][2] = src[i]->z; }
+}
+static grt::ir::CameraConfig fromC(const GrtCameraConfig* o) {
+    grt::ir::CameraConfig c;
+    c.AspectRatio = o->AspectRatio; c.Width = o->Width; c.SamplesPerPixel = o->SamplesPerPixel; c.MaxDepth = o->MaxDepth; c.MaxThreads = o->MaxThreads;
+    c.VerticalFOV = o->VerticalFOV; c.DefocusAngle = o->DefocusAngle; c.FocusDistance = o->FocusDistance;
+    c.Background = v3(o->Background); c.MaxContribution = o->MaxContribution;
+    c.lookFrom = v3(o->lookFrom); c.lookAt = v3(o->lookAt); c.vup = v3(o->vup);
+    return c;
+}
+
+int grt_host_builtin_scene(GrtHostScene* s, int scene_id, const GrtSceneOptions* opt, GrtCameraConfig* cam) {
+    if (!s || !cam) return fail("NULL argument");
+    grt::scenes::SceneOptions o;
+    if (opt) {
+        o.width = opt->width; o.spp = opt->spp; o.aspect = opt->aspect; o.seed = opt->seed; o.mesh_segments = opt->mesh_segments;
+        o.image_rgb = opt->image_rgb; o.image_w = opt->image_w; o.image_h = opt->image_h;
+    }
+    grt::ir::CameraConfig c;
+    try {
+        if (!grt::scenes::buildScene(scene_id, s->ir, c, o)) return fail("unknown scene id (main.go -S accepts 1..8; the default scene is empty)");
+    } catch (const std::exception& ex) { return fail(ex.what()); }
+    toC(c, cam);
+    return 0;
+}
+
+int grt_host_flatten(GrtHostScene* s, GrtScene* out) {
+    if (!s || !out) return fail("NULL argument");
+    s->flat.reset(new grt::flat::FlatScene());
+    grt::flat::Flattener f(s->ir);
+    if (!f.run(*s->flat)) { s->flat.reset(); return fail(f.error); }
+    *out = s->flat->view();
+    return 0;
+}
+
+int grt_host_camera_derive(const GrtCameraConfig* cfg, GrtCamera* out) {
+    if (!cfg || !out) return fail("NULL argument");
+    std::string err;
+    if (!grt::flat::deriveCamera(fromC(cfg), *out, err)) return fail(err);
+    return 0;
+}
+
+long grt_host_write_ppm(const uint8_t* rgb8, int width, int height, char* out, long cap) {
+    if (!rgb8 || !out || cap < 32) return -1;
+    long n = snprintf(out, (size_t)cap, "P3\n%d %d\n255\n", width, height);   // camera.go:160
+    // "%d %d %d\n" per pixel, color.go:45 — hand-rolled, this is 10^6..10^7 lines
+    static const char digits[] = "0123456789";
+    for (long i = 0; i < (long)width * height; i++) {
+        if (n + 13 > cap) return -1;
+        for (int k = 0; k < 3; k++) {
+            unsigned v = rgb8[3 * i + k];
+            if (v >= 100) { out[n++] = digits[v / 100]; out[n++] = digits[(v / 10) % 10]; out[n++] = digits[v % 10]; }
+            else if (v >= 10) { out[n++] = digits[v / 10]; out[n++] = digits[v % 10]; }
+            else out[n++] = digits[v];
+            out[n++] = k == 2 ? '\n' : ' ';
+        }
+    }
+    if (n < cap) out[n] = 0;
+    return n;
+}
+
+int grt_host_camera_render(GrtHostScene* s, const GrtCameraConfig* cfg, uint64_t seed, int variant, int n_gpus,
+                           float* rgb_sum_out, char* ppm_out, long ppm_cap, long* ppm_len, double* kernel_ms) {
+    if (!s || !cfg) { fail("NULL argument"); return GRT_E_INVALID; }
+    GrtScene scene;
+    if (grt_host_flatten(s, &scene)) return GRT_E_INVALID;
+    GrtCamera cam;
+    if (grt_host_camera_derive(cfg, &cam)) return GRT_E_INVALID;
+    GrtOptions opt;
+    memset(&opt, 0, sizeof(opt));
+    opt.seed = seed; opt.variant = variant; opt.sample_stride = 1;
+    size_t nval = (size_t)cam.width * cam.height * 3;
+    std::vector<float> sum(nval, 0.0f);
+    std::vector<uint8_t> rgb8(nval, 0);
+    int rc;
+    if (n_gpus <= 1) {
+        GrtSceneHandle h = nullptr;
+        rc = grt_scene_upload(&scene, 0, &h);
+        if (rc) { fail(grt_last_error()); return rc; }
+        rc = grt_render(h, &cam, &opt, sum.data(), rgb8.data(), nullptr);
+        grt_scene_free(h);
+        if (kernel_ms) *kernel_ms = 0;
+    } else {
+        std::vector<int> devs(n_gpus);
+        for (int i = 0; i < n_gpus; i++) devs[i] = i;
+        rc = grt_render_multi(&scene, &cam, &opt, devs.data(), n_gpus, sum.data(), rgb8.data(), kernel_ms);
+    }
+    if (rc) { fail(grt_last_error()); return rc; }
+    if (rgb_sum_out) memcpy(rgb_sum_out, sum.data(), nval * sizeof(float));
+    if (ppm_out) {
+        long n = grt_host_write_ppm(rgb8.data(), cam.width, cam.height, ppm_out, ppm_cap);
+        if (n < 0) { fail("ppm buffer too small"); return GRT_E_INVALID; }
+        if (ppm_len) *ppm_len = n;
+    }
+    return GRT_OK;
+}
+
+const void* grt_host_scene_description(GrtHostScene* s) { return s ? &s->ir : nullptr; }
+
+}  // extern "C"
