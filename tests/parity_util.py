@@ -1,0 +1,61 @@
+"""Shared helpers for the parity tests: ray batches and comparison against the oracle."""
+import numpy as np
+import go_raytracer_b200 as g
+from oracle import oracle_py as O
+
+NO_ID = 0xFFFFFFFF
+INF = np.float32(np.inf)
+
+
+def make_rays(o, d, time=None, tmin=0.001, tmax=np.inf, self_id=None):
+    n = len(o)
+    r = np.zeros(n, dtype=g.RAY_DTYPE)
+    r["o"] = np.asarray(o, dtype=np.float32)
+    r["d"] = np.asarray(d, dtype=np.float32)
+    r["tmin"] = np.float32(tmin)
+    r["tmax"] = np.float32(tmax)
+    r["time"] = 0 if time is None else np.asarray(time, dtype=np.float32)
+    r["self_id"] = NO_ID if self_id is None else np.asarray(self_id, dtype=np.uint32)
+    return r
+
+
+def primary_batch(cfg, window, sample=0, seed=0xC0FFEE):
+    """Camera rays of getRay (camera.go:256-270) for stratum `sample`, rounded to fp32 (the common input)."""
+    o, d, t = O.primary_rays(cfg, seed, window, sample)
+    return make_rays(o, d, t)
+
+
+def secondary_batch(orc_hits, rng, time=None, around_normal=True):
+    """Rays leaving the oracle's first-bounce hit points: origin on a primitive (self_id set)."""
+    ok = orc_hits["id"] >= 0
+    p = orc_hits["p"][ok]
+    n = orc_hits["n"][ok]
+    v = rng.normal(size=p.shape)
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    if around_normal:
+        # hemisphere around the face-forwarded normal, like a diffuse bounce; unnormalised lengths like light samples
+        flip = np.sum(v * n, axis=1) < 0
+        v[flip] *= -1
+    v *= rng.uniform(0.3, 300.0, size=(len(v), 1))
+    tm = None if time is None else np.asarray(time)[ok]
+    return make_rays(p, v, tm, self_id=orc_hits["id"][ok].astype(np.uint32))
+
+
+def compare_hits(gpu, orc, audit=True, t_rel=1e-5):
+    """Parity checks 1 and 2: ids bit-exact except documented ties/edges (flags), t within t_rel."""
+    gid = gpu["id"].astype(np.int64)
+    gid[gpu["id"] == NO_ID] = -1
+    oid = orc["id"].astype(np.int64)
+    flagged = orc["flags"] != 0 if audit else np.zeros(len(orc), bool)
+    id_mismatch = (gid != oid)
+    bad_id = id_mismatch & ~flagged
+    both = (gid >= 0) & (oid >= 0) & ~id_mismatch
+    rel = np.zeros(len(orc))
+    rel[both] = np.abs(gpu["t"][both].astype(np.float64) - orc["t"][both]) / np.maximum(np.abs(orc["t"][both]), 1e-30)
+    bad_t = both & (rel > t_rel) & ~flagged
+    return {
+        "n": len(orc), "hits": int((oid >= 0).sum()), "flagged": int(flagged.sum()),
+        "id_mismatch_total": int(id_mismatch.sum()), "id_mismatch_unflagged": int(bad_id.sum()),
+        "t_max_rel_unflagged": float(rel[both & ~flagged].max()) if (both & ~flagged).any() else 0.0,
+        "t_bad": int(bad_t.sum()), "bad_id_idx": np.nonzero(bad_id)[0][:10], "bad_t_idx": np.nonzero(bad_t)[0][:10],
+    }
