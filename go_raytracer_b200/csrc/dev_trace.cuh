@@ -136,24 +136,27 @@ __device__ __forceinline__ bool sphere_hit(const GrtSphere& s, const RayD& r, fl
 }
 
 // ---- quad.Hit + isInterior, objects.go:167-206 -----------------------------
+// `excl`: object id of the primitive the ray starts on — a planar primitive cannot be re-hit
+// by a ray leaving it (the fp64 reference finds t ~ 1e-13 < tmin there), so it is skipped.
 template <uint32_t FEAT>
-__device__ __forceinline__ bool quad_hit(const GrtQuad* q, const RayD& r, float tmin, float tmax, float& t_out, float& a_out, float& b_out) {
+__device__ __forceinline__ bool quad_hit(const GrtQuad* q, const RayD& r, float tmin, float tmax, uint32_t excl, float& t_out, float& a_out, float& b_out) {
     const float4 q0 = *(const float4*)&q->n[0];   // n, D
     const float4 q1 = *(const float4*)&q->Q[0];   // Q, flags
+    const float4 q3 = *(const float4*)&q->B[0];   // B, id
+    if (__float_as_uint(q3.w) == excl) return false;
     float t;
     if (!(FEAT & F_ROTQUAD) || (__float_as_uint(q1.w) & GRT_QUAD_AXIS_ALIGNED)) {
         float denom = q0.x * r.d.x + q0.y * r.d.y + q0.z * r.d.z;
         if (fabsf(denom) < 1e-8f) return false;
-        t = (q0.w - (q0.x * r.o.x + q0.y * r.o.y + q0.z * r.o.z)) / denom;
+        t = __fdividef(q0.w - (q0.x * r.o.x + q0.y * r.o.y + q0.z * r.o.z), denom);   // 2 ulp, well inside the 1e-5 budget
     } else {
         double denom = q->n64[0] * r.d64.x + q->n64[1] * r.d64.y + q->n64[2] * r.d64.z;
         if (fabs(denom) < 1e-8) return false;
         double num = q->D64 - (q->n64[0] * r.o64.x + q->n64[1] * r.o64.y + q->n64[2] * r.o64.z);
-        t = (float)num / (float)denom;
+        t = __fdividef((float)num, (float)denom);
     }
     if (!(tmin <= t && t <= tmax)) return false;   // Contains: closed interval (objects.go:177)
     const float4 q2 = *(const float4*)&q->A[0];
-    const float4 q3 = *(const float4*)&q->B[0];
     float px = fmaf(t, r.d.x, r.o.x) - q1.x, py = fmaf(t, r.d.y, r.o.y) - q1.y, pz = fmaf(t, r.d.z, r.o.z) - q1.z;
     float alpha = q2.x * px + q2.y * py + q2.z * pz;
     float beta = q3.x * px + q3.y * py + q3.z * pz;
@@ -195,59 +198,77 @@ struct MediumRngCtx {
 };
 
 // Closest-hit traversal.  Visits children left first, right second
-// (bvh.go:73-79); the current closest t plays the role of rayT.Max.  List
-// items are visited in list order (hittable.go:129-136) through a
-// continuation entry so a long list never overflows the stack.
+// (bvh.go:73-79); the current closest t plays the role of rayT.Max.  A list
+// (HittableList, or a collapsed BVH subtree) is scanned in order in a tight
+// loop (hittable.go:129-136); a non-primitive item parks the rest of the list
+// on the stack as a continuation entry, so a long list never overflows it.
 template <uint32_t FEAT, bool BOUNDARY, bool STATS>
 __device__ bool closest_hit(const SceneView& sv, uint32_t root, const RayD& r, float tmin, float tmax,
-                                         uint32_t self_id, MediumRngCtx* mrng, HitInfo& hit, TraceCounters* tc) {
+                            uint32_t self_id, MediumRngCtx* mrng, HitInfo& hit, TraceCounters* tc) {
     constexpr int STACK = BOUNDARY ? GRT_STACK_BOUNDARY : GRT_STACK_MAIN;
     uint32_t stack[STACK];
     int sp = 0;
     stack[sp++] = root;
     bool any = false;
     const float4* nodes = sv.nodes();
+    const uint32_t excl = BOUNDARY ? GRT_NO_ID : self_id;
+
+    // one primitive test; returns true when `ref` was a primitive (tested or compiled out)
+    auto test_prim = [&](uint32_t ref) -> bool {
+        const uint32_t type = GRT_REF_TYPE(ref), idx = ref & GRT_REF_MASK;
+        if ((FEAT & F_QUAD) && type == GRT_REF_QUAD) {
+            const GrtQuad* q = sv.quads() + idx;
+            if (STATS) tc->quad++;
+            float t, a, b;
+            if (quad_hit<FEAT>(q, r, tmin, tmax, excl, t, a, b)) { any = true; tmax = t; hit.t = t; hit.ref = ref; hit.u = a; hit.v = b; }
+            return true;
+        }
+        if ((FEAT & F_SPHERE) && type == GRT_REF_SPHERE) {
+            const GrtSphere& s = sv.spheres()[idx];
+            if (STATS) tc->sphere++;
+            float t;
+            if (sphere_hit(s, r, tmin, tmax, s.id == excl, t)) { any = true; tmax = t; hit.t = t; hit.ref = ref; hit.u = 0; hit.v = 0; }
+            return true;
+        }
+        if ((FEAT & F_TRI) && type == GRT_REF_TRI) {
+            if (STATS) tc->tri++;
+            float t, u, v;
+            if (tri_hit(sv.ds->tris + idx, r, tmin, tmax, excl, t, u, v)) { any = true; tmax = t; hit.t = t; hit.ref = ref; hit.u = u; hit.v = v; }
+            return true;
+        }
+        return type == GRT_REF_QUAD || type == GRT_REF_SPHERE || type == GRT_REF_TRI || type == GRT_REF_NONE;
+    };
+
     while (sp > 0) {
         uint32_t ref = stack[--sp];
         uint32_t type = GRT_REF_TYPE(ref);
         uint32_t idx = ref & GRT_REF_MASK;
         if ((FEAT & F_LIST) && type == GRT_REF_LIST) {
-            // continuation: visit items()[idx], then the rest of the list
-            uint32_t item = sv.items()[idx];
-            if (!(item & GRT_LIST_LAST)) stack[sp++] = GRT_MAKE_REF(GRT_REF_LIST, idx + 1);
-            ref = item & ~GRT_LIST_LAST;
+            const uint32_t* items = sv.items();
+            for (;;) {
+                const uint32_t item = items[idx];
+                const bool last = (item & GRT_LIST_LAST) != 0;
+                ref = item & ~GRT_LIST_LAST;
+                if (test_prim(ref)) {
+                    if (last) { ref = GRT_MAKE_REF(GRT_REF_NONE, 0); break; }
+                    idx++;
+                    continue;
+                }
+                if (!last) stack[sp++] = GRT_MAKE_REF(GRT_REF_LIST, idx + 1);   // the rest of the list, after this item
+                break;
+            }
             type = GRT_REF_TYPE(ref);
             idx = ref & GRT_REF_MASK;
-            if (type == GRT_REF_LIST) { stack[sp++] = ref; continue; }  // nested list
+            if (type == GRT_REF_LIST) { stack[sp++] = ref; continue; }   // nested list
+            if (type == GRT_REF_NONE) continue;
         }
-        if (type == GRT_REF_NODE) {
+        if ((FEAT & F_NODE) && type == GRT_REF_NODE) {
             float4 n0 = nodes[2 * idx], n1 = nodes[2 * idx + 1];
             if (STATS) tc->box++;
             if (!box_hit(n0, n1, r, tmin, tmax)) continue;
             uint32_t l = __float_as_uint(n1.z), rr = __float_as_uint(n1.w);
             stack[sp++] = rr;
             stack[sp++] = l;
-            continue;
-        }
-        if ((FEAT & F_QUAD) && type == GRT_REF_QUAD) {
-            const GrtQuad* q = sv.quads() + idx;
-            if (STATS) tc->quad++;
-            if (!BOUNDARY && q->id == self_id) continue;   // planar: an exact-arithmetic ray cannot re-hit it
-            float t, a, b;
-            if (quad_hit<FEAT>(q, r, tmin, tmax, t, a, b)) { any = true; tmax = t; hit.t = t; hit.ref = ref; hit.u = a; hit.v = b; }
-            continue;
-        }
-        if ((FEAT & F_SPHERE) && type == GRT_REF_SPHERE) {
-            const GrtSphere& s = sv.spheres()[idx];
-            if (STATS) tc->sphere++;
-            float t;
-            if (sphere_hit(s, r, tmin, tmax, !BOUNDARY && s.id == self_id, t)) { any = true; tmax = t; hit.t = t; hit.ref = ref; hit.u = 0; hit.v = 0; }
-            continue;
-        }
-        if ((FEAT & F_TRI) && type == GRT_REF_TRI) {
-            if (STATS) tc->tri++;
-            float t, u, v;
-            if (tri_hit(sv.ds->tris + idx, r, tmin, tmax, BOUNDARY ? GRT_NO_ID : self_id, t, u, v)) { any = true; tmax = t; hit.t = t; hit.ref = ref; hit.u = u; hit.v = v; }
             continue;
         }
         if (!BOUNDARY && (FEAT & F_MEDIUM) && type == GRT_REF_MEDIUM) {
@@ -271,7 +292,7 @@ __device__ bool closest_hit(const SceneView& sv, uint32_t root, const RayD& r, f
             any = true; tmax = t; hit.t = t; hit.ref = ref; hit.u = 0; hit.v = 0;
             continue;
         }
-        // GRT_REF_NONE or a type compiled out: never hits
+        test_prim(ref);   // a primitive that is a direct BVH child (bvh.go:73,79), or NONE
     }
     return any;
 }

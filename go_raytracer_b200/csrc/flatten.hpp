@@ -112,9 +112,19 @@ struct FlatScene {
     }
 };
 
+// Flatten-time tuning (results are identical for every setting; only the amount
+// of box culling changes).  A BVH subtree with few leaves costs more to
+// traverse on SIMT hardware (divergent box/primitive alternation) than to test
+// linearly, so such subtrees are emitted as a HittableList-style ordered run of
+// their leaves in the reference's depth-first, left-first visiting order.
+struct FlattenOptions {
+    int collapse_whole = 32;   // a BuildBVH result with at most this many leaves becomes one list
+    int collapse_leaf = 4;     // inside larger trees, subtrees with at most this many leaves become lists
+};
+
 class Flattener {
    public:
-    explicit Flattener(const ir::Scene& s) : S(s) {}
+    explicit Flattener(const ir::Scene& s, FlattenOptions o = FlattenOptions()) : S(s), opt(o) {}
     std::string error;
 
     bool run(FlatScene& out) {
@@ -137,14 +147,28 @@ class Flattener {
 
    private:
     const ir::Scene& S;
+    FlattenOptions opt;
     FlatScene* F = nullptr;
     std::vector<RefBox> refBoxCache;
     std::vector<char> refBoxDone;
     int mediumNeed = 0;
 
     // ---- BuildBVH topology in object space (bvh.go:35-61) ---------------
-    struct BuildNode { int left, right; bool leftIsNode, rightIsNode; };  // child: build-node index or hittable id
+    struct BuildNode { int left, right; bool leftIsNode, rightIsNode; int leaves; };  // child: build-node index or hittable id
     struct Topology { std::vector<BuildNode> nodes; int root = -1; };
+
+    // number of primitive tests a linear run over this hittable would make (-1: not collapsible)
+    int leafCount(int hid) {
+        const ir::Hittable& h = S.hittables[hid];
+        switch (h.type) {
+            case ir::H_SPHERE: case ir::H_QUAD: case ir::H_TRI: return 1;
+            case ir::H_MEDIUM: return 1;   // stays a single ref inside a run
+            case ir::H_TRANSLATE: case ir::H_ROTATEY: return leafCount(h.child);
+            case ir::H_LIST: { int n = 0; for (int c : S.lists[h.a]) { int k = leafCount(c); n += k; if (n > (1 << 20)) return 1 << 20; } return n; }
+            case ir::H_BVH: return topology(h.a).nodes[topology(h.a).root].leaves;
+        }
+        return 1;
+    }
     std::map<int, Topology> topoCache;  // by list payload index
 
     // Reference bbox of a hittable in ITS OWN space (what obj.BBox() returns in Go).
@@ -230,8 +254,8 @@ class Flattener {
         int axis = longestAxis(bb);
         size_t span = end - start;
         BuildNode n;
-        if (span == 1) { n.left = n.right = objs[start]; n.leftIsNode = n.rightIsNode = false; }
-        else if (span == 2) { n.left = objs[start]; n.right = objs[start + 1]; n.leftIsNode = n.rightIsNode = false; }
+        if (span == 1) { n.left = n.right = objs[start]; n.leftIsNode = n.rightIsNode = false; n.leaves = leafCount(objs[start]); }
+        else if (span == 2) { n.left = objs[start]; n.right = objs[start + 1]; n.leftIsNode = n.rightIsNode = false; n.leaves = leafCount(objs[start]) + leafCount(objs[start + 1]); }
         else {
             // boxCompare (bvh.go:25-32).  Go's sort.Slice is not stable; equal keys are
             // documented as unordered, we keep list order for them.
@@ -244,6 +268,7 @@ class Flattener {
             n.left = buildRange(T, objs, start, mid);
             n.right = buildRange(T, objs, mid, end);
             n.leftIsNode = n.rightIsNode = true;
+            n.leaves = T.nodes[n.left].leaves + T.nodes[n.right].leaves;
         }
         T.nodes.push_back(n);
         return (int)T.nodes.size() - 1;
@@ -265,7 +290,7 @@ class Flattener {
         void add(V3 p) { double v[3] = {p.x, p.y, p.z}; for (int a = 0; a < 3; a++) { lo[a] = std::fmin(lo[a], v[a]); hi[a] = std::fmax(hi[a], v[a]); } }
         void add(const WBox& b) { for (int a = 0; a < 3; a++) { lo[a] = std::fmin(lo[a], b.lo[a]); hi[a] = std::fmax(hi[a], b.hi[a]); } }
     };
-    struct Emitted { uint32_t ref; WBox box; int need; };
+    struct Emitted { uint32_t ref; WBox box; int need; bool spliceable = false; uint32_t list_first = 0, list_count = 0; };
 
     static float roundDown(double x) {
         if (x == -kInf) return -std::numeric_limits<float>::infinity();
@@ -280,8 +305,61 @@ class Flattener {
         return std::nextafterf(f, std::numeric_limits<float>::infinity());
     }
 
+    // Leaves of a subtree in the order BVHNode.Hit visits them (left first).  A span-1 node
+    // names the same object twice (bvh.go:44-46); testing a surface primitive twice cannot
+    // change the closest hit, so it is listed once — a constantMedium draws a fresh random
+    // number per test (medium.go:47) and is therefore kept twice.
+    void collectLeaves(const Topology& T, int ni, std::vector<int>& out) {
+        const BuildNode& bn = T.nodes[ni];
+        if (bn.leftIsNode) collectLeaves(T, bn.left, out); else out.push_back(bn.left);
+        if (bn.rightIsNode) collectLeaves(T, bn.right, out);
+        else if (bn.leftIsNode || bn.right != bn.left || S.hittables[bn.right].type == ir::H_MEDIUM) out.push_back(bn.right);
+    }
+    // Emits an ordered run of hittables as one list; nested lists are spliced in place
+    // (HittableList.Hit of a nested list is the same sequential scan, hittable.go:122-138).
+    Emitted emitRun(const std::vector<int>& kids, const Xform& X, bool inBoundary) {
+        Emitted e;
+        e.need = 0;
+        std::vector<Emitted> ch;
+        for (int c : kids) ch.push_back(emit(c, X, inBoundary));
+        std::vector<uint32_t> refs;
+        int need = 0;
+        for (size_t i = 0; i < ch.size(); i++) {
+            e.box.add(ch[i].box);
+            uint32_t r = ch[i].ref;
+            if (GRT_REF_TYPE(r) == GRT_REF_NONE) continue;
+            if (GRT_REF_TYPE(r) == GRT_REF_LIST && ch[i].spliceable) {
+                // splice: the child's items were appended most recently and contain only leaf refs
+                for (uint32_t k = ch[i].list_first; k < ch[i].list_first + ch[i].list_count; k++) refs.push_back(F->items[k] & ~GRT_LIST_LAST);
+                continue;
+            }
+            refs.push_back(r);
+            need = std::max(need, 1 + ch[i].need);
+        }
+        if (refs.empty()) { e.ref = GRT_MAKE_REF(GRT_REF_NONE, 0); return e; }
+        uint32_t first = (uint32_t)F->items.size();
+        bool leafOnly = true;
+        for (size_t i = 0; i < refs.size(); i++) {
+            uint32_t t = GRT_REF_TYPE(refs[i]);
+            if (t != GRT_REF_SPHERE && t != GRT_REF_QUAD && t != GRT_REF_TRI) leafOnly = false;
+            F->items.push_back(refs[i] | (i + 1 == refs.size() ? GRT_LIST_LAST : 0u));
+        }
+        e.ref = GRT_MAKE_REF(GRT_REF_LIST, first);
+        e.need = std::max(need, 2);
+        e.spliceable = leafOnly;
+        e.list_first = first;
+        e.list_count = (uint32_t)refs.size();
+        return e;
+    }
+
     Emitted emitTopo(const Topology& T, int ni, const Xform& X, bool inBoundary) {
         const BuildNode& bn = T.nodes[ni];
+        int limit = (T.nodes[T.root].leaves <= opt.collapse_whole) ? opt.collapse_whole : opt.collapse_leaf;
+        if (bn.leaves <= limit && bn.leaves > 0) {
+            std::vector<int> leaves;
+            collectLeaves(T, ni, leaves);
+            return emitRun(leaves, X, inBoundary);
+        }
         uint32_t idx = (uint32_t)F->nodes.size();
         if (idx > GRT_REF_MASK) throw std::runtime_error("too many BVH nodes");
         F->nodes.emplace_back();  // depth-first, left-first order
@@ -385,26 +463,7 @@ class Flattener {
                 break;
             }
             case ir::H_LIST: {
-                const std::vector<int>& kids = S.lists[h.a];
-                if (kids.empty()) {
-                    // an empty HittableList never hits; represent it as NONE
-                    e.ref = GRT_MAKE_REF(GRT_REF_NONE, 0);
-                    break;
-                }
-                std::vector<Emitted> ch;
-                for (int c : kids) ch.push_back(emit(c, X, inBoundary));
-                uint32_t first = (uint32_t)F->items.size();
-                for (size_t i = 0; i < ch.size(); i++) {
-                    F->items.push_back(ch[i].ref | (i + 1 == ch.size() ? GRT_LIST_LAST : 0u));
-                    e.box.add(ch[i].box);
-                }
-                e.ref = GRT_MAKE_REF(GRT_REF_LIST, first);
-                int need = 0;
-                for (size_t i = 0; i < ch.size(); i++) {
-                    bool last = i + 1 == ch.size();
-                    need = std::max(need, std::max(last ? 1 : 2, (last ? 0 : 1) + ch[i].need));
-                }
-                e.need = need;
+                e = emitRun(S.lists[h.a], X, inBoundary);
                 break;
             }
             case ir::H_BVH: {
