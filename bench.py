@@ -199,7 +199,7 @@ def run_ours(args):
     # per step: scene upload (H2D), zeroed host accumulation buffer up, render, reduce, tonemap, sums + rgb8 down
     flat = s.flatten()
     scene_bytes = (flat.n_nodes * 32 + flat.n_spheres * 64 + flat.n_quads * 96 + flat.n_tris * 48 + flat.n_items * 4 +
-                   flat.n_media * 16 + flat.n_materials * 32 + flat.n_textures * 32 + flat.n_lights * 208)
+                   flat.n_media * 16 + flat.n_materials * 32 + flat.n_textures * 32 + flat.n_lights * 304)
     h_sum = torch.zeros(nval, dtype=torch.float32).pin_memory()
     h_rgb8 = torch.zeros(nval, dtype=torch.uint8).pin_memory()
     h_zero = torch.zeros(nval, dtype=torch.float32).pin_memory()

@@ -210,6 +210,29 @@ __device__ __forceinline__ double light_pdf(const GrtLight* L, d3 o, d3 d) {
     return 0;
 }
 
+// fp32 fast path of the quad light pdf.  Returns 1 with *pdf set when the fp32 result is
+// certain (the hit is at least 1e-4 inside / outside every decision boundary: alpha, beta in
+// [0,1], t >= 0.001, |denom| >= 1e-8), 0 when the decision is within fp32 error of a boundary
+// and the fp64 evaluation must be used.
+__device__ __forceinline__ int quad_light_pdf_fast(const GrtLight* L, f3 o, f3 d, float* pdf) {
+    const float* f = L->f;
+    const f3 n = ld3(f + 9);
+    const float denom = dot(n, d);
+    const float t = __fdividef(f[15] - dot(n, o), denom);
+    const f3 planar = (o + d * t) - ld3(f);
+    const f3 w = ld3(f + 12);
+    const float alpha = dot(w, cross(planar, ld3(f + 6)));
+    const float beta = dot(w, cross(ld3(f + 3), planar));
+    const float dd = dot(d, d);
+    const float EPS = 1e-4f;
+    const bool grazing = fabsf(denom) < 1e-3f * sqrtf(dd);
+    const bool inside = (alpha > EPS) & (alpha < 1.0f - EPS) & (beta > EPS) & (beta < 1.0f - EPS) & (t > 0.002f);
+    const bool outside = (alpha < -EPS) | (alpha > 1.0f + EPS) | (beta < -EPS) | (beta > 1.0f + EPS) | (t < 0.0005f);
+    if (grazing || !(inside || outside)) return 0;   // NaNs land here too
+    *pdf = inside ? (t * t * dd) / (fabsf(denom) * rsqrtf(dd) * f[16]) : 0.0f;
+    return 1;
+}
+
 // ---- vec.go sampling routines -------------------------------------------------
 __device__ __forceinline__ f3 random_unit_vector(Rng& rng) {  // vec.go:159-167
     for (;;) {
@@ -316,31 +339,43 @@ __device__ __forceinline__ ShadeResult shade_vertex(const SceneView& sv, const R
     f3 att = texture_value<FEAT>(sv, m.tex, s.u, s.v, s.p);
     const uint32_t nl = sv.ds->n_lights;
     const GrtLight* lights = sv.lights();
-    d3 p64 = tod3(s.p);
     f3 wn = unit(s.n);   // onb.W
     f3 dir;
-    d3 dir64;
+    bool from_light = false;
+    uint32_t li = 0;
+    float r1 = 0, r2 = 0;
     if (rng.next() < 0.5f) {  // pdf.go:69-74: p[0] = light
         if (sv.ds->lights_mode == GRT_LIGHTS_LIST && nl == 0) {  // hittable.go:98-101: vec.Random()
             float x = rng.next(), y = rng.next(), z = rng.next();
-            dir = mk3(x, y, z); dir64 = tod3(dir);
+            dir = mk3(x, y, z);
         } else {
-            uint32_t li = 0;
             if (sv.ds->lights_mode == GRT_LIGHTS_LIST) { li = (uint32_t)(rng.next() * (float)nl); if (li >= nl) li = nl - 1; }  // rand.Intn
-            float r1 = rng.next(), r2 = rng.next();
-            dir64 = light_random<FEAT>(lights + li, p64, r1, r2);
-            dir = tof3(dir64);
+            r1 = rng.next(); r2 = rng.next();
+            from_light = true;
+            const GrtLight* L = lights + li;
+            if ((FEAT & F_QUAD_LIGHT) && L->type == GRT_LIGHT_QUAD) dir = (ld3(L->f) + ld3(L->f + 3) * r1 + ld3(L->f + 6) * r2) - s.p;   // objects.go:161-165
+            else dir = tof3(light_random<FEAT>(L, tod3(s.p), r1, r2));
         }
     } else {
         if (iso) dir = random_unit_vector(rng);                                   // pdf.go:21-23
-        else { float r1 = rng.next(), r2 = rng.next(); Onb b = make_onb(s.n); dir = onb_transform(b, random_cosine_direction(r1, r2)); }  // pdf.go:38-40
-        dir64 = tod3(dir);
+        else { float c1 = rng.next(), c2 = rng.next(); Onb b = make_onb(s.n); dir = onb_transform(b, random_cosine_direction(c1, c2)); }  // pdf.go:38-40
     }
     // mixPdf.Value: 0.5 * lights.PdfValue + 0.5 * material pdf  (pdf.go:65-67, hittable.go:89-96)
-    double lp = 0.0;
+    float lp = 0.0f;
     if (nl > 0) {
-        double weight = 1.0 / (double)nl;
-        for (uint32_t i = 0; i < nl; i++) lp += weight * light_pdf<FEAT>(lights + i, p64, dir64);
+        const float weight = 1.0f / (float)nl;
+        for (uint32_t i = 0; i < nl; i++) {
+            const GrtLight* L = lights + i;
+            float pv;
+            if (!((FEAT & F_QUAD_LIGHT) && L->type == GRT_LIGHT_QUAD && quad_light_pdf_fast(L, s.p, dir, &pv))) {
+                // within fp32 error of a decision boundary (or not a quad): the reference's fp64 arithmetic.
+                // A direction sampled ON this light is regenerated in fp64 so that it cannot fall off its edge.
+                d3 p64 = tod3(s.p);
+                d3 dir64 = (from_light && i == li) ? light_random<FEAT>(L, p64, r1, r2) : tod3(dir);
+                pv = (float)light_pdf<FEAT>(L, p64, dir64);
+            }
+            lp += weight * pv;
+        }
         if (n_lightpdf) *n_lightpdf += nl;
     }
     float mp, sp;
@@ -350,7 +385,7 @@ __device__ __forceinline__ ShadeResult shade_vertex(const SceneView& sv, const R
         mp = fmaxf(0.0f, cosTheta / GRT_PI_F);               // pdf.go:33-36
         sp = cosTheta < 0 ? 0.0f : cosTheta / GRT_PI_F;      // materials.go:51-57
     }
-    float pdfValue = 0.5f * (float)lp + 0.5f * mp;
+    float pdfValue = 0.5f * lp + 0.5f * mp;
     if (pdfValue == 0.0f && sp == 0.0f) { R.kind = SHADE_NAN; R.value = mk3(0, 0, 0); return R; }  // 0 * x * (1/0) = NaN (camera.go:328)
     R.kind = SHADE_DIFFUSE;
     R.value = att * (sp / pdfValue);

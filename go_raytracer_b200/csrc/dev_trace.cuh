@@ -20,7 +20,7 @@ enum : uint32_t {
     F_DEFOCUS = 1u << 13, F_NODE = 1u << 14,
     F_ALL = (1u << 15) - 1
 };
-#define GRT_NEEDS_F64(FEAT) (((FEAT) & (F_SPHERE | F_ROTQUAD)) != 0)
+#define GRT_NEEDS_F64(FEAT) (((FEAT) & F_SPHERE) != 0)
 
 // The small, hot arrays live in one blob (byte offsets below) so a block can
 // stage the whole thing in shared memory when it fits; large arrays stay in HBM.
@@ -44,7 +44,8 @@ struct SceneView {
     __device__ __forceinline__ const float4* nodes() const { return (const float4*)(base + ds->off_nodes); }
     __device__ __forceinline__ const GrtSphere* spheres() const { return (const GrtSphere*)(base + ds->off_spheres); }
     __device__ __forceinline__ const GrtQuad* quads() const { return (const GrtQuad*)(base + ds->off_quads); }
-    __device__ __forceinline__ const uint32_t* items() const { return (const uint32_t*)(base + ds->off_items); }
+    // run-length list entries built at upload: x = first ref (| GRT_LIST_LAST), y = number of consecutive primitives
+    __device__ __forceinline__ const uint2* entries() const { return (const uint2*)(base + ds->off_items); }
     __device__ __forceinline__ const GrtMedium* media() const { return (const GrtMedium*)(base + ds->off_media); }
     __device__ __forceinline__ const GrtMaterial* materials() const { return (const GrtMaterial*)(base + ds->off_materials); }
     __device__ __forceinline__ const GrtTexture* textures() const { return (const GrtTexture*)(base + ds->off_textures); }
@@ -71,7 +72,7 @@ struct RayD {
 template <uint32_t FEAT>
 __device__ __forceinline__ void ray_setup(RayD& r, f3 o, f3 d, float time) {
     r.o = o; r.d = d; r.time = time;
-    r.invd = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);  // aabb.go:96
+    if (FEAT & F_NODE) r.invd = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);  // aabb.go:96 (only box tests use it)
     if (GRT_NEEDS_F64(FEAT)) {
         r.o64 = tod3(o); r.d64 = tod3(d);
         r.a64 = dot(r.d64, r.d64);
@@ -136,33 +137,35 @@ __device__ __forceinline__ bool sphere_hit(const GrtSphere& s, const RayD& r, fl
 }
 
 // ---- quad.Hit + isInterior, objects.go:167-206 -----------------------------
-// `excl`: object id of the primitive the ray starts on — a planar primitive cannot be re-hit
-// by a ray leaving it (the fp64 reference finds t ~ 1e-13 < tmin there), so it is skipped.
-template <uint32_t FEAT>
+// Branch-free fp32 candidate test.  `excl`: object id of the primitive the ray
+// starts on — a planar primitive cannot be re-hit by a ray leaving it (the
+// fp64 reference finds t ~ 1e-13 < tmin there), so it is skipped.
+// For a quad that is not axis-aligned the fp32 plane distance D - n.o loses
+// relative accuracy when the origin is close to the plane; the WINNING hit is
+// therefore refined in fp64 by quad_refine_t (one refinement per segment
+// instead of fp64 arithmetic in every test).
 __device__ __forceinline__ bool quad_hit(const GrtQuad* q, const RayD& r, float tmin, float tmax, uint32_t excl, float& t_out, float& a_out, float& b_out) {
     const float4 q0 = *(const float4*)&q->n[0];   // n, D
     const float4 q1 = *(const float4*)&q->Q[0];   // Q, flags
+    const float4 q2 = *(const float4*)&q->A[0];   // A, mat
     const float4 q3 = *(const float4*)&q->B[0];   // B, id
-    if (__float_as_uint(q3.w) == excl) return false;
-    float t;
-    if (!(FEAT & F_ROTQUAD) || (__float_as_uint(q1.w) & GRT_QUAD_AXIS_ALIGNED)) {
-        float denom = q0.x * r.d.x + q0.y * r.d.y + q0.z * r.d.z;
-        if (fabsf(denom) < 1e-8f) return false;
-        t = __fdividef(q0.w - (q0.x * r.o.x + q0.y * r.o.y + q0.z * r.o.z), denom);   // 2 ulp, well inside the 1e-5 budget
-    } else {
-        double denom = q->n64[0] * r.d64.x + q->n64[1] * r.d64.y + q->n64[2] * r.d64.z;
-        if (fabs(denom) < 1e-8) return false;
-        double num = q->D64 - (q->n64[0] * r.o64.x + q->n64[1] * r.o64.y + q->n64[2] * r.o64.z);
-        t = __fdividef((float)num, (float)denom);
-    }
-    if (!(tmin <= t && t <= tmax)) return false;   // Contains: closed interval (objects.go:177)
-    const float4 q2 = *(const float4*)&q->A[0];
-    float px = fmaf(t, r.d.x, r.o.x) - q1.x, py = fmaf(t, r.d.y, r.o.y) - q1.y, pz = fmaf(t, r.d.z, r.o.z) - q1.z;
-    float alpha = q2.x * px + q2.y * py + q2.z * pz;
-    float beta = q3.x * px + q3.y * py + q3.z * pz;
-    if (!(0.0f <= alpha && alpha <= 1.0f) || !(0.0f <= beta && beta <= 1.0f)) return false;  // objects.go:199
+    const float denom = q0.x * r.d.x + q0.y * r.d.y + q0.z * r.d.z;
+    const float num = q0.w - (q0.x * r.o.x + q0.y * r.o.y + q0.z * r.o.z);
+    const float t = __fdividef(num, denom);        // 2 ulp, far inside the 1e-5 budget
+    const float px = fmaf(t, r.d.x, r.o.x) - q1.x, py = fmaf(t, r.d.y, r.o.y) - q1.y, pz = fmaf(t, r.d.z, r.o.z) - q1.z;
+    const float alpha = q2.x * px + q2.y * py + q2.z * pz;
+    const float beta = q3.x * px + q3.y * py + q3.z * pz;
+    const bool ok = (fabsf(denom) >= 1e-8f) & (tmin <= t) & (t <= tmax)            // objects.go:171,177 (closed interval)
+                    & (0.0f <= alpha) & (alpha <= 1.0f) & (0.0f <= beta) & (beta <= 1.0f)   // objects.go:199
+                    & (__float_as_uint(q3.w) != excl);
     t_out = t; a_out = alpha; b_out = beta;
-    return true;
+    return ok;
+}
+__device__ __forceinline__ float quad_refine_t(const GrtQuad* q, const RayD& r, float t32) {
+    if (q->flags & GRT_QUAD_AXIS_ALIGNED) return t32;   // D - n.o and n.d are single-rounding there
+    const double denom = q->n64[0] * (double)r.d.x + q->n64[1] * (double)r.d.y + q->n64[2] * (double)r.d.z;
+    const double num = q->D64 - (q->n64[0] * (double)r.o.x + q->n64[1] * (double)r.o.y + q->n64[2] * (double)r.o.z);
+    return __fdividef((float)num, (float)denom);
 }
 
 // ---- Triangle.Hit (Möller–Trumbore), objects.go:408-461 --------------------
@@ -213,27 +216,33 @@ __device__ bool closest_hit(const SceneView& sv, uint32_t root, const RayD& r, f
     const float4* nodes = sv.nodes();
     const uint32_t excl = BOUNDARY ? GRT_NO_ID : self_id;
 
-    // one primitive test; returns true when `ref` was a primitive (tested or compiled out)
-    auto test_prim = [&](uint32_t ref) -> bool {
+    // n consecutive primitives starting at `ref`; returns true when `ref` names a primitive type
+    auto test_prims = [&](uint32_t ref, uint32_t n) -> bool {
         const uint32_t type = GRT_REF_TYPE(ref), idx = ref & GRT_REF_MASK;
         if ((FEAT & F_QUAD) && type == GRT_REF_QUAD) {
             const GrtQuad* q = sv.quads() + idx;
-            if (STATS) tc->quad++;
-            float t, a, b;
-            if (quad_hit<FEAT>(q, r, tmin, tmax, excl, t, a, b)) { any = true; tmax = t; hit.t = t; hit.ref = ref; hit.u = a; hit.v = b; }
+            if (STATS) tc->quad += n;
+            for (uint32_t k = 0; k < n; k++, q++) {
+                float t, a, b;
+                if (quad_hit(q, r, tmin, tmax, excl, t, a, b)) { any = true; tmax = t; hit.t = t; hit.ref = ref + k; hit.u = a; hit.v = b; }
+            }
             return true;
         }
         if ((FEAT & F_SPHERE) && type == GRT_REF_SPHERE) {
-            const GrtSphere& s = sv.spheres()[idx];
-            if (STATS) tc->sphere++;
-            float t;
-            if (sphere_hit(s, r, tmin, tmax, s.id == excl, t)) { any = true; tmax = t; hit.t = t; hit.ref = ref; hit.u = 0; hit.v = 0; }
+            const GrtSphere* s = sv.spheres() + idx;
+            if (STATS) tc->sphere += n;
+            for (uint32_t k = 0; k < n; k++, s++) {
+                float t;
+                if (sphere_hit(*s, r, tmin, tmax, s->id == excl, t)) { any = true; tmax = t; hit.t = t; hit.ref = ref + k; hit.u = 0; hit.v = 0; }
+            }
             return true;
         }
         if ((FEAT & F_TRI) && type == GRT_REF_TRI) {
-            if (STATS) tc->tri++;
-            float t, u, v;
-            if (tri_hit(sv.ds->tris + idx, r, tmin, tmax, excl, t, u, v)) { any = true; tmax = t; hit.t = t; hit.ref = ref; hit.u = u; hit.v = v; }
+            if (STATS) tc->tri += n;
+            for (uint32_t k = 0; k < n; k++) {
+                float t, u, v;
+                if (tri_hit(sv.ds->tris + idx + k, r, tmin, tmax, excl, t, u, v)) { any = true; tmax = t; hit.t = t; hit.ref = ref + k; hit.u = u; hit.v = v; }
+            }
             return true;
         }
         return type == GRT_REF_QUAD || type == GRT_REF_SPHERE || type == GRT_REF_TRI || type == GRT_REF_NONE;
@@ -244,12 +253,12 @@ __device__ bool closest_hit(const SceneView& sv, uint32_t root, const RayD& r, f
         uint32_t type = GRT_REF_TYPE(ref);
         uint32_t idx = ref & GRT_REF_MASK;
         if ((FEAT & F_LIST) && type == GRT_REF_LIST) {
-            const uint32_t* items = sv.items();
+            const uint2* entries = sv.entries();
             for (;;) {
-                const uint32_t item = items[idx];
-                const bool last = (item & GRT_LIST_LAST) != 0;
-                ref = item & ~GRT_LIST_LAST;
-                if (test_prim(ref)) {
+                const uint2 e = entries[idx];
+                const bool last = (e.x & GRT_LIST_LAST) != 0;
+                ref = e.x & ~GRT_LIST_LAST;
+                if (test_prims(ref, e.y)) {
                     if (last) { ref = GRT_MAKE_REF(GRT_REF_NONE, 0); break; }
                     idx++;
                     continue;
@@ -292,8 +301,9 @@ __device__ bool closest_hit(const SceneView& sv, uint32_t root, const RayD& r, f
             any = true; tmax = t; hit.t = t; hit.ref = ref; hit.u = 0; hit.v = 0;
             continue;
         }
-        test_prim(ref);   // a primitive that is a direct BVH child (bvh.go:73,79), or NONE
+        test_prims(ref, 1);   // a primitive that is a direct BVH child (bvh.go:73,79), or NONE
     }
+    if ((FEAT & F_ROTQUAD) && any && GRT_REF_TYPE(hit.ref) == GRT_REF_QUAD) hit.t = quad_refine_t(sv.quads() + (hit.ref & GRT_REF_MASK), r, hit.t);
     return any;
 }
 

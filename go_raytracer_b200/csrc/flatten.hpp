@@ -587,6 +587,7 @@ class Flattener {
                 // log.Fatal("hit an invalid PDF function") (hittable.go:69-72)
                 throw std::runtime_error("lights must be spheres, quads or triangles (reference: hit an invalid PDF function)");
         }
+        for (int i = 0; i < 24; i++) L.f[i] = (float)L.p[i];
         F->lights.push_back(L);
     }
     void emitLights() {

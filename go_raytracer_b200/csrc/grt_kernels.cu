@@ -414,7 +414,40 @@ extern "C" int grt_scene_upload(const GrtScene* s, int device, GrtSceneHandle* o
     ds.off_nodes = place(s->n_nodes * (uint32_t)sizeof(GrtNode));
     ds.off_spheres = place(s->n_spheres * (uint32_t)sizeof(GrtSphere));
     ds.off_quads = place(s->n_quads * (uint32_t)sizeof(GrtQuad));
-    ds.off_items = place(s->n_items * 4u);
+    // run-length list entries (device-internal): consecutive items of one primitive type with
+    // consecutive indices collapse into {first ref, count}; LIST refs are remapped to entry indices
+    std::vector<uint32_t> item2entry(s->n_items + 1, 0);
+    std::vector<uint32_t> entries;   // pairs
+    for (uint32_t i = 0; i < s->n_items;) {
+        uint32_t ref = s->items[i] & ~GRT_LIST_LAST;
+        uint32_t t = GRT_REF_TYPE(ref);
+        bool prim = t == GRT_REF_SPHERE || t == GRT_REF_QUAD || t == GRT_REF_TRI;
+        uint32_t n = 1;
+        item2entry[i] = (uint32_t)(entries.size() / 2);
+        bool last = (s->items[i] & GRT_LIST_LAST) != 0;
+        while (prim && !last && i + n < s->n_items) {
+            uint32_t nx = s->items[i + n] & ~GRT_LIST_LAST;
+            if (nx != ref + n) break;
+            item2entry[i + n] = (uint32_t)(entries.size() / 2);   // only list STARTS are ever referenced
+            last = (s->items[i + n] & GRT_LIST_LAST) != 0;
+            n++;
+        }
+        entries.push_back(ref | (last ? GRT_LIST_LAST : 0u));
+        entries.push_back(n);
+        i += n;
+    }
+    auto remap = [&](uint32_t ref) -> uint32_t {
+        uint32_t flag = ref & GRT_LIST_LAST, r = ref & ~GRT_LIST_LAST;
+        if (GRT_REF_TYPE(r) == GRT_REF_LIST) r = GRT_MAKE_REF(GRT_REF_LIST, item2entry[r & GRT_REF_MASK]);
+        return r | flag;
+    };
+    for (size_t k = 0; k < entries.size(); k += 2) entries[k] = remap(entries[k]);
+    std::vector<GrtNode> nodes(s->nodes, s->nodes + s->n_nodes);
+    for (auto& n : nodes) { n.left = remap(n.left); n.right = remap(n.right); }
+    std::vector<GrtMedium> media(s->media, s->media + s->n_media);
+    for (auto& m : media) m.boundary = remap(m.boundary);
+    const uint32_t n_entries = (uint32_t)(entries.size() / 2);
+    ds.off_items = place(n_entries * 8u);
     ds.off_media = place(s->n_media * (uint32_t)sizeof(GrtMedium));
     ds.off_materials = place(s->n_materials * (uint32_t)sizeof(GrtMaterial));
     ds.off_textures = place(s->n_textures * (uint32_t)sizeof(GrtTexture));
@@ -423,20 +456,20 @@ extern "C" int grt_scene_upload(const GrtScene* s, int device, GrtSceneHandle* o
     if (off == 0) off = 16;
     std::vector<unsigned char> blob(off, 0);
     auto put = [&](uint32_t o, const void* p, size_t bytes) { if (bytes) memcpy(blob.data() + o, p, bytes); };
-    put(ds.off_nodes, s->nodes, s->n_nodes * sizeof(GrtNode));
+    put(ds.off_nodes, nodes.data(), s->n_nodes * sizeof(GrtNode));
     put(ds.off_spheres, s->spheres, s->n_spheres * sizeof(GrtSphere));
     put(ds.off_quads, s->quads, s->n_quads * sizeof(GrtQuad));
-    put(ds.off_items, s->items, s->n_items * 4u);
-    put(ds.off_media, s->media, s->n_media * sizeof(GrtMedium));
+    put(ds.off_items, entries.data(), n_entries * 8u);
+    put(ds.off_media, media.data(), s->n_media * sizeof(GrtMedium));
     put(ds.off_materials, s->materials, s->n_materials * sizeof(GrtMaterial));
     put(ds.off_textures, s->textures, s->n_textures * sizeof(GrtTexture));
     put(ds.off_lights, s->lights, s->n_lights * sizeof(GrtLight));
     put(ds.off_images, s->images, s->n_images * sizeof(GrtImage));
     ds.blob_bytes = off;
-    ds.n_nodes = s->n_nodes; ds.n_spheres = s->n_spheres; ds.n_quads = s->n_quads; ds.n_items = s->n_items; ds.n_media = s->n_media;
+    ds.n_nodes = s->n_nodes; ds.n_spheres = s->n_spheres; ds.n_quads = s->n_quads; ds.n_items = n_entries; ds.n_media = s->n_media;
     ds.n_materials = s->n_materials; ds.n_textures = s->n_textures; ds.n_lights = s->n_lights; ds.n_images = s->n_images;
     ds.n_tris = s->n_tris; ds.n_perlins = s->n_perlins;
-    ds.root = s->root; ds.lights_mode = s->lights_mode; ds.stack_need = s->max_depth_hint;
+    ds.root = remap(s->root); ds.lights_mode = s->lights_mode; ds.stack_need = s->max_depth_hint;
     ds.features = scan_features(s);
     auto upload = [&](void** dptr, const void* src, size_t bytes) -> int {
         *dptr = nullptr;
@@ -479,7 +512,7 @@ unsigned int* grt_internal_counter(GrtSceneHandle h) { return h->d_counter; }
 
 // ---- feature-variant dispatch ------------------------------------------------
 // Each variant is a feature SUPERSET compiled as its own kernel.
-#define V_CORNELL (F_NODE | F_QUAD | F_LIST | F_ROTQUAD | F_QUAD_LIGHT)
+#define V_CORNELL (F_QUAD | F_LIST | F_ROTQUAD | F_QUAD_LIGHT)
 #define V_SMOKE (V_CORNELL | F_MEDIUM | F_ISOTROPIC)
 #define V_SPHERES (F_NODE | F_SPHERE | F_LIST | F_SPECULAR | F_TEXTURE | F_SPHERE_LIGHT | F_DEFOCUS)
 #define V_MESH (F_NODE | F_SPHERE | F_TRI | F_LIST | F_SPECULAR | F_SPHERE_LIGHT | F_TRI_LIGHT | F_TRISHADE | F_DEFOCUS)

@@ -165,7 +165,7 @@ typedef struct GrtPerlin {
 #define GRT_LIGHT_SPHERE 1u
 #define GRT_LIGHT_QUAD   2u
 #define GRT_LIGHT_TRI    3u
-typedef struct GrtLight {            /* 208 B */
+typedef struct GrtLight {            /* 304 B */
     uint32_t type;
     uint32_t prim;                   /* ref of the primitive in the world (or NONE) */
     uint32_t flags;                  /* tri: GRT_TRI_HAS_NORMALS            */
@@ -174,6 +174,7 @@ typedef struct GrtLight {            /* 208 B */
      * quad:   Q[3], u[3], v[3], n[3], w[3], D, area
      * tri:    v0[3], v1[3], v2[3], area, n0[3], n1[3], n2[3]               */
     double   p[24];
+    float    f[24];                  /* p[] rounded to fp32: fast path, falls back to p[] near an edge */
 } GrtLight;
 
 #define GRT_LIGHTS_LIST 0u           /* lights is a HittableList (hittable.go:89-103) */
