@@ -242,9 +242,8 @@ __device__ __forceinline__ f3 random_unit_vector(Rng& rng) {  // vec.go:159-167
     }
 }
 __device__ __forceinline__ f3 random_cosine_direction(float r1, float r2) {  // vec.go:177-186
-    float phi = 2 * GRT_PI_F * r1;
     float sn, cs;
-    sincosf(phi, &sn, &cs);
+    sincospif(2.0f * r1, &sn, &cs);   // phi = 2 pi r1
     float sr = sqrtf(r2);
     return mk3(cs * sr, sn * sr, sqrtf(1 - r2));
 }
@@ -269,7 +268,10 @@ __device__ __forceinline__ void camera_ray(const DevCamera& cam, int px, int py,
     Rng rng;
     rng.init(pixel_index, sample, 0, GRT_STREAM_CAMERA, k0, k1);
     // renderRow calls getRay(j, row, s_j, s_i) (camera.go:97-99): the x stratum is the inner loop index
-    int s_x = (int)(sample % (uint32_t)cam.spp_sqrt), s_y = (int)(sample / (uint32_t)cam.spp_sqrt);
+    uint32_t s_y;
+    if (cam.spp_sqrt <= 1024) s_y = (uint32_t)(((float)sample + 0.5f) * cam.recip_spp_sqrt);   // exact: sample < 2^20, margin 0.5/S
+    else s_y = sample / (uint32_t)cam.spp_sqrt;
+    const uint32_t s_x = sample - s_y * (uint32_t)cam.spp_sqrt;
     float ox = (((float)s_x + rng.next()) * cam.recip_spp_sqrt) - 0.5f;   // sampleSquareStratified :277-282
     float oy = (((float)s_y + rng.next()) * cam.recip_spp_sqrt) - 0.5f;
     f3 rel = cam.p00_rel + cam.du * ((float)px + ox) + cam.dv * ((float)py + oy);   // pixelSample - center
@@ -358,7 +360,13 @@ __device__ __forceinline__ ShadeResult shade_vertex(const SceneView& sv, const R
         }
     } else {
         if (iso) dir = random_unit_vector(rng);                                   // pdf.go:21-23
-        else { float c1 = rng.next(), c2 = rng.next(); Onb b = make_onb(s.n); dir = onb_transform(b, random_cosine_direction(c1, c2)); }  // pdf.go:38-40
+        else {  // pdf.go:38-40
+            float c1 = rng.next(), c2 = rng.next();
+            Onb b;
+            if (s.has_onb) { b.u = s.ou; b.v = s.front ? s.ov : -s.ov; b.w = s.n; }   // NewONB(-n) = (u, -v, -n)
+            else b = make_onb(s.n);
+            dir = onb_transform(b, random_cosine_direction(c1, c2));
+        }
     }
     // mixPdf.Value: 0.5 * lights.PdfValue + 0.5 * material pdf  (pdf.go:65-67, hittable.go:89-96)
     float lp = 0.0f;
@@ -382,13 +390,13 @@ __device__ __forceinline__ ShadeResult shade_vertex(const SceneView& sv, const R
     if (iso) { mp = 1.0f / (4 * GRT_PI_F); sp = mp; }
     else {
         float cosTheta = dot(unit(dir), wn);
-        mp = fmaxf(0.0f, cosTheta / GRT_PI_F);               // pdf.go:33-36
-        sp = cosTheta < 0 ? 0.0f : cosTheta / GRT_PI_F;      // materials.go:51-57
+        mp = fmaxf(0.0f, cosTheta * (1.0f / GRT_PI_F));               // pdf.go:33-36
+        sp = cosTheta < 0 ? 0.0f : cosTheta * (1.0f / GRT_PI_F);      // materials.go:51-57
     }
     float pdfValue = 0.5f * lp + 0.5f * mp;
     if (pdfValue == 0.0f && sp == 0.0f) { R.kind = SHADE_NAN; R.value = mk3(0, 0, 0); return R; }  // 0 * x * (1/0) = NaN (camera.go:328)
     R.kind = SHADE_DIFFUSE;
-    R.value = att * (sp / pdfValue);
+    R.value = att * __fdividef(sp, pdfValue);
     R.dir = dir;
     return R;
 }

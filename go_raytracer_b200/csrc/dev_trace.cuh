@@ -18,16 +18,30 @@ enum : uint32_t {
     F_SPECULAR = 1u << 5, F_TEXTURE = 1u << 6, F_ISOTROPIC = 1u << 7, F_ROTQUAD = 1u << 8,
     F_SPHERE_LIGHT = 1u << 9, F_QUAD_LIGHT = 1u << 10, F_TRI_LIGHT = 1u << 11, F_TRISHADE = 1u << 12,
     F_DEFOCUS = 1u << 13, F_NODE = 1u << 14,
-    F_ALL = (1u << 15) - 1
+    F_DUPIDS = 1u << 15,   // some object id names more than one flat primitive: exclude by id, not by flat ref
+    F_ALL = (1u << 16) - 1
 };
 #define GRT_NEEDS_F64(FEAT) (((FEAT) & F_SPHERE) != 0)
+
+// Device-internal quad records, repacked from GrtQuad at upload.
+// Hot (48 B, read by every test): plane, and the interior test folded into two affine forms
+//   alpha = A.xyz . p + A.w   (A.w = -A.Q),   beta = B.xyz . p + B.w
+// Cold (80 B, read once per hit): normal, the precomputed orthonormal basis of onb.go:13-25 for
+// the FRONT-face normal (the back face is (u, -v, -n)), ids, and the fp64 plane for refinement.
+struct DQuadHot { float4 plane, A, B; };
+struct DQuadCold {
+    float n[3]; uint32_t flags;
+    float ou[3]; uint32_t mat;
+    float ov[3]; uint32_t id;
+    double n64[3]; double D64;
+};
 
 // The small, hot arrays live in one blob (byte offsets below) so a block can
 // stage the whole thing in shared memory when it fits; large arrays stay in HBM.
 struct DevScene {
     const unsigned char* blob;   // HBM copy of the blob
     uint32_t blob_bytes;
-    uint32_t off_nodes, off_spheres, off_quads, off_items, off_media, off_materials, off_textures, off_lights, off_images;
+    uint32_t off_nodes, off_spheres, off_quads, off_quads_cold, off_items, off_media, off_materials, off_textures, off_lights, off_images;
     uint32_t n_nodes, n_spheres, n_quads, n_items, n_media, n_materials, n_textures, n_lights, n_images;
     const GrtTri* tris;          // HBM
     const GrtTriShade* tri_shade;
@@ -43,7 +57,8 @@ struct SceneView {
     const DevScene* ds;
     __device__ __forceinline__ const float4* nodes() const { return (const float4*)(base + ds->off_nodes); }
     __device__ __forceinline__ const GrtSphere* spheres() const { return (const GrtSphere*)(base + ds->off_spheres); }
-    __device__ __forceinline__ const GrtQuad* quads() const { return (const GrtQuad*)(base + ds->off_quads); }
+    __device__ __forceinline__ const DQuadHot* quads() const { return (const DQuadHot*)(base + ds->off_quads); }
+    __device__ __forceinline__ const DQuadCold* quads_cold() const { return (const DQuadCold*)(base + ds->off_quads_cold); }
     // run-length list entries built at upload: x = first ref (| GRT_LIST_LAST), y = number of consecutive primitives
     __device__ __forceinline__ const uint2* entries() const { return (const uint2*)(base + ds->off_items); }
     __device__ __forceinline__ const GrtMedium* media() const { return (const GrtMedium*)(base + ds->off_media); }
@@ -137,31 +152,25 @@ __device__ __forceinline__ bool sphere_hit(const GrtSphere& s, const RayD& r, fl
 }
 
 // ---- quad.Hit + isInterior, objects.go:167-206 -----------------------------
-// Branch-free fp32 candidate test.  `excl`: object id of the primitive the ray
-// starts on — a planar primitive cannot be re-hit by a ray leaving it (the
-// fp64 reference finds t ~ 1e-13 < tmin there), so it is skipped.
-// For a quad that is not axis-aligned the fp32 plane distance D - n.o loses
-// relative accuracy when the origin is close to the plane; the WINNING hit is
-// therefore refined in fp64 by quad_refine_t (one refinement per segment
-// instead of fp64 arithmetic in every test).
-__device__ __forceinline__ bool quad_hit(const GrtQuad* q, const RayD& r, float tmin, float tmax, uint32_t excl, float& t_out, float& a_out, float& b_out) {
-    const float4 q0 = *(const float4*)&q->n[0];   // n, D
-    const float4 q1 = *(const float4*)&q->Q[0];   // Q, flags
-    const float4 q2 = *(const float4*)&q->A[0];   // A, mat
-    const float4 q3 = *(const float4*)&q->B[0];   // B, id
-    const float denom = q0.x * r.d.x + q0.y * r.d.y + q0.z * r.d.z;
-    const float num = q0.w - (q0.x * r.o.x + q0.y * r.o.y + q0.z * r.o.z);
+// Branch-free fp32 candidate test on the 48-byte hot record.  For a quad that
+// is not axis-aligned the fp32 plane distance D - n.o loses relative accuracy
+// when the origin is close to the plane; the WINNING hit is therefore refined
+// in fp64 by quad_refine_t (one refinement per segment instead of fp64
+// arithmetic in every test).
+__device__ __forceinline__ bool quad_hit(const DQuadHot* q, const RayD& r, float tmin, float tmax, float& t_out, float& a_out, float& b_out) {
+    const float4 P = q->plane, A = q->A, B = q->B;
+    const float denom = P.x * r.d.x + P.y * r.d.y + P.z * r.d.z;
+    const float num = P.w - (P.x * r.o.x + P.y * r.o.y + P.z * r.o.z);
     const float t = __fdividef(num, denom);        // 2 ulp, far inside the 1e-5 budget
-    const float px = fmaf(t, r.d.x, r.o.x) - q1.x, py = fmaf(t, r.d.y, r.o.y) - q1.y, pz = fmaf(t, r.d.z, r.o.z) - q1.z;
-    const float alpha = q2.x * px + q2.y * py + q2.z * pz;
-    const float beta = q3.x * px + q3.y * py + q3.z * pz;
+    const float px = fmaf(t, r.d.x, r.o.x), py = fmaf(t, r.d.y, r.o.y), pz = fmaf(t, r.d.z, r.o.z);
+    const float alpha = fmaf(A.x, px, fmaf(A.y, py, fmaf(A.z, pz, A.w)));
+    const float beta = fmaf(B.x, px, fmaf(B.y, py, fmaf(B.z, pz, B.w)));
     const bool ok = (fabsf(denom) >= 1e-8f) & (tmin <= t) & (t <= tmax)            // objects.go:171,177 (closed interval)
-                    & (0.0f <= alpha) & (alpha <= 1.0f) & (0.0f <= beta) & (beta <= 1.0f)   // objects.go:199
-                    & (__float_as_uint(q3.w) != excl);
+                    & (0.0f <= alpha) & (alpha <= 1.0f) & (0.0f <= beta) & (beta <= 1.0f);   // objects.go:199
     t_out = t; a_out = alpha; b_out = beta;
     return ok;
 }
-__device__ __forceinline__ float quad_refine_t(const GrtQuad* q, const RayD& r, float t32) {
+__device__ __forceinline__ float quad_refine_t(const DQuadCold* q, const RayD& r, float t32) {
     if (q->flags & GRT_QUAD_AXIS_ALIGNED) return t32;   // D - n.o and n.d are single-rounding there
     const double denom = q->n64[0] * (double)r.d.x + q->n64[1] * (double)r.d.y + q->n64[2] * (double)r.d.z;
     const double num = q->D64 - (q->n64[0] * (double)r.o.x + q->n64[1] * (double)r.o.y + q->n64[2] * (double)r.o.z);
@@ -206,8 +215,11 @@ struct MediumRngCtx {
 // loop (hittable.go:129-136); a non-primitive item parks the rest of the list
 // on the stack as a continuation entry, so a long list never overflows it.
 template <uint32_t FEAT, bool BOUNDARY, bool STATS>
+// Self exclusion: the primitive the ray starts on is named by its object id (`self_id`, the C ABI's
+// notion) and by its flat ref (`self_ref`).  When every object id maps to one flat primitive the cheap
+// ref comparison is used; with F_DUPIDS the id of every candidate is compared.
 __device__ bool closest_hit(const SceneView& sv, uint32_t root, const RayD& r, float tmin, float tmax,
-                            uint32_t self_id, MediumRngCtx* mrng, HitInfo& hit, TraceCounters* tc) {
+                            uint32_t self_id, uint32_t self_ref, MediumRngCtx* mrng, HitInfo& hit, TraceCounters* tc) {
     constexpr int STACK = BOUNDARY ? GRT_STACK_BOUNDARY : GRT_STACK_MAIN;
     uint32_t stack[STACK];
     int sp = 0;
@@ -215,16 +227,22 @@ __device__ bool closest_hit(const SceneView& sv, uint32_t root, const RayD& r, f
     bool any = false;
     const float4* nodes = sv.nodes();
     const uint32_t excl = BOUNDARY ? GRT_NO_ID : self_id;
+    const uint32_t excl_ref = BOUNDARY ? 0xFFFFFFFFu : self_ref;
 
     // n consecutive primitives starting at `ref`; returns true when `ref` names a primitive type
     auto test_prims = [&](uint32_t ref, uint32_t n) -> bool {
         const uint32_t type = GRT_REF_TYPE(ref), idx = ref & GRT_REF_MASK;
         if ((FEAT & F_QUAD) && type == GRT_REF_QUAD) {
-            const GrtQuad* q = sv.quads() + idx;
+            const DQuadHot* q = sv.quads() + idx;
             if (STATS) tc->quad += n;
-            for (uint32_t k = 0; k < n; k++, q++) {
+#pragma unroll 2
+            for (uint32_t k = 0; k < n; k++) {
                 float t, a, b;
-                if (quad_hit(q, r, tmin, tmax, excl, t, a, b)) { any = true; tmax = t; hit.t = t; hit.ref = ref + k; hit.u = a; hit.v = b; }
+                bool ok = quad_hit(q + k, r, tmin, tmax, t, a, b);
+                // a planar primitive cannot be re-hit by a ray leaving it (the fp64 reference finds t ~ 1e-13 < tmin)
+                if (FEAT & F_DUPIDS) ok = ok && (sv.quads_cold()[idx + k].id != excl);
+                else ok = ok & ((ref + k) != excl_ref);
+                if (ok) { any = true; tmax = t; hit.t = t; hit.ref = ref + k; hit.u = a; hit.v = b; }
             }
             return true;
         }
@@ -286,8 +304,8 @@ __device__ bool closest_hit(const SceneView& sv, uint32_t root, const RayD& r, f
             if (STATS) tc->medium++;
             HitInfo h1, h2;
             const float INF = __int_as_float(0x7f800000);
-            if (!closest_hit<FEAT, true, STATS>(sv, m.boundary, r, -INF, INF, GRT_NO_ID, nullptr, h1, tc)) continue;
-            if (!closest_hit<FEAT, true, STATS>(sv, m.boundary, r, h1.t + 0.0001f, INF, GRT_NO_ID, nullptr, h2, tc)) continue;
+            if (!closest_hit<FEAT, true, STATS>(sv, m.boundary, r, -INF, INF, GRT_NO_ID, 0xFFFFFFFFu, nullptr, h1, tc)) continue;
+            if (!closest_hit<FEAT, true, STATS>(sv, m.boundary, r, h1.t + 0.0001f, INF, GRT_NO_ID, 0xFFFFFFFFu, nullptr, h2, tc)) continue;
             float t1 = fmaxf(h1.t, tmin), t2 = fminf(h2.t, tmax);
             if (t1 >= t2) continue;
             t1 = fmaxf(0.0f, t1);
@@ -303,7 +321,7 @@ __device__ bool closest_hit(const SceneView& sv, uint32_t root, const RayD& r, f
         }
         test_prims(ref, 1);   // a primitive that is a direct BVH child (bvh.go:73,79), or NONE
     }
-    if ((FEAT & F_ROTQUAD) && any && GRT_REF_TYPE(hit.ref) == GRT_REF_QUAD) hit.t = quad_refine_t(sv.quads() + (hit.ref & GRT_REF_MASK), r, hit.t);
+    if ((FEAT & F_ROTQUAD) && any && GRT_REF_TYPE(hit.ref) == GRT_REF_QUAD) hit.t = quad_refine_t(sv.quads_cold() + (hit.ref & GRT_REF_MASK), r, hit.t);
     return any;
 }
 
@@ -315,6 +333,8 @@ struct Surface {
     bool front;
     bool is_surface;    // false for a medium scatter point
     bool planar;
+    bool has_onb;       // ou/ov hold the precomputed basis of the FRONT normal (quads)
+    f3 ou, ov;
 };
 
 __device__ __forceinline__ void set_face_normal(Surface& s, f3 d, f3 outward) {  // hittable.go:27-34
@@ -339,12 +359,13 @@ __device__ __forceinline__ void finish_hit(const SceneView& sv, const RayD& r, c
     uint32_t type = GRT_REF_TYPE(h.ref), idx = h.ref & GRT_REF_MASK;
     s.p = mk3(fmaf(h.t, r.d.x, r.o.x), fmaf(h.t, r.d.y, r.o.y), fmaf(h.t, r.d.z, r.o.z));  // Ray.At, ray.go:35
     s.u = h.u; s.v = h.v;
-    s.is_surface = true; s.planar = true;
+    s.is_surface = true; s.planar = true; s.has_onb = false;
     if ((FEAT & F_QUAD) && type == GRT_REF_QUAD) {
-        const GrtQuad* q = sv.quads() + idx;
-        const float4 q0 = *(const float4*)&q->n[0];
-        s.mat = q->mat; s.id = q->id;
-        set_face_normal(s, r.d, mk3(q0.x, q0.y, q0.z));
+        const float4* c = (const float4*)(sv.quads_cold() + idx);
+        const float4 c0 = c[0], c1 = c[1], c2 = c[2];
+        s.mat = __float_as_uint(c1.w); s.id = __float_as_uint(c2.w);
+        set_face_normal(s, r.d, mk3(c0.x, c0.y, c0.z));
+        s.has_onb = true; s.ou = mk3(c1.x, c1.y, c1.z); s.ov = mk3(c2.x, c2.y, c2.z);
         return;
     }
     if ((FEAT & F_SPHERE) && type == GRT_REF_SPHERE) {

@@ -17,6 +17,8 @@
 #include <vector>
 #include <atomic>
 #include <mutex>
+#include <algorithm>
+#include <math.h>
 
 #include "dev_shade.cuh"
 #include "grt_internal.h"
@@ -62,7 +64,7 @@ __global__ void __launch_bounds__(128) trace_batch_kernel(const __grid_constant_
     mr.pixel = (uint32_t)i; mr.sample = (uint32_t)(i >> 32); mr.bounce = 0; mr.k0 = 0; mr.k1 = 0; mr.count = 0;
     HitInfo h;
     GrtHit out;
-    if (closest_hit<FEAT, false, false>(sv, ds.root, r, a.w, b.w, self_id, &mr, h, nullptr)) {
+    if (closest_hit<FEAT | F_DUPIDS, false, false>(sv, ds.root, r, a.w, b.w, self_id, 0xFFFFFFFFu, &mr, h, nullptr)) {
         Surface s;
         finish_hit<FEAT>(sv, r, h, true, s);
         out.t = h.t; out.id = s.id; out.ref = h.ref; out.front_face = s.front ? 1u : 0u;
@@ -133,15 +135,22 @@ __global__ void __launch_bounds__(GRT_MEGA_THREADS, GRT_MEGA_MIN_BLOCKS) render_
         if (blk_next < blk_end) return blk_next++;
         return 0xffffffffu;
     };
+    // pixel coordinates packed as (y << 16) | x, one integer division per PIXEL instead of per path
+    auto pixel_xy = [&](uint32_t q) -> uint32_t {
+        if (q == 0xffffffffu) return 0u;
+        uint32_t row = q / (uint32_t)P.ww;
+        return (((uint32_t)P.y0 + row) << 16) | ((uint32_t)P.x0 + (q - row * (uint32_t)P.ww));
+    };
     pix_cur = claim_pixel();
     if (pix_cur == 0xffffffffu) return;
+    uint32_t xy_cur = pixel_xy(pix_cur), xy_nxt = 0;
 
     // lane state
     bool active = false;
     uint32_t my_parity = 0;                  // 0: my path belongs to pix_cur, 1: to pix_nxt
     f3 acc0 = mk3(0, 0, 0), acc1 = mk3(0, 0, 0);
     RayD ray;
-    uint32_t self_id = GRT_NO_ID, my_sample = 0, my_pixel_index = 0;
+    uint32_t self_id = GRT_NO_ID, self_ref = 0xFFFFFFFFu, my_sample = 0, my_pixel_index = 0;
     int bounce = 0;
     f3 head = mk3(1, 1, 1), wtop = mk3(0, 0, 0);
     int sp = 0;
@@ -163,12 +172,13 @@ __global__ void __launch_bounds__(GRT_MEGA_THREADS, GRT_MEGA_MIN_BLOCKS) render_
                 uint32_t k = k_alloc + rank;
                 my_sample = P.sample_first + k * P.sample_stride;
                 my_parity = alloc_on_nxt ? 1u : 0u;
-                int px = P.x0 + (int)(pix_alloc % (uint32_t)P.ww), py = P.y0 + (int)(pix_alloc / (uint32_t)P.ww);
+                const uint32_t xy = alloc_on_nxt ? xy_nxt : xy_cur;   // warp-uniform, computed once per pixel
+                int px = (int)(xy & 0xffffu), py = (int)(xy >> 16);
                 my_pixel_index = (uint32_t)(py * cam.width + px);
                 f3 o, d; float time;
                 camera_ray<FEAT>(cam, px, py, my_sample, my_pixel_index, P.k0, P.k1, o, d, time);
                 ray_setup<FEAT>(ray, o, d, time);
-                self_id = GRT_NO_ID; bounce = 0; head = mk3(1, 1, 1); sp = 0;
+                self_id = GRT_NO_ID; self_ref = 0xFFFFFFFFu; bounce = 0; head = mk3(1, 1, 1); sp = 0;
                 active = true;
                 if (STATS) st_paths++;
             }
@@ -178,7 +188,7 @@ __global__ void __launch_bounds__(GRT_MEGA_THREADS, GRT_MEGA_MIN_BLOCKS) render_
             if (!need) break;
             // this pixel is used up: move allocation to the next pixel, at most one ahead
             if (alloc_on_nxt) break;
-            if (pix_nxt == 0xffffffffu) pix_nxt = claim_pixel();
+            if (pix_nxt == 0xffffffffu) { pix_nxt = claim_pixel(); xy_nxt = pixel_xy(pix_nxt); }
             if (pix_nxt == 0xffffffffu) break;
             alloc_on_nxt = true; k_alloc = 0;
         }
@@ -194,14 +204,14 @@ __global__ void __launch_bounds__(GRT_MEGA_THREADS, GRT_MEGA_MIN_BLOCKS) render_
                 s.z += __shfl_xor_sync(FULL, s.z, off);
             }
             if (lane == 0) {
-                int px = P.x0 + (int)(pix_cur % (uint32_t)P.ww), py = P.y0 + (int)(pix_cur / (uint32_t)P.ww);
+                int px = (int)(xy_cur & 0xffffu), py = (int)(xy_cur >> 16);
                 float* dst = P.rgb_sum + ((size_t)py * cam.width + px) * 3;
                 dst[0] += s.x; dst[1] += s.y; dst[2] += s.z;   // this warp owns the pixel for the whole launch
             }
             acc0 = acc1; acc1 = mk3(0, 0, 0);
             if (active) my_parity = 0u;   // survivors were on pix_nxt
-            if (alloc_on_nxt) { pix_cur = pix_nxt; pix_nxt = 0xffffffffu; alloc_on_nxt = false; }
-            else { pix_cur = claim_pixel(); k_alloc = 0; }
+            if (alloc_on_nxt) { pix_cur = pix_nxt; xy_cur = xy_nxt; pix_nxt = 0xffffffffu; alloc_on_nxt = false; }
+            else { pix_cur = claim_pixel(); xy_cur = pixel_xy(pix_cur); k_alloc = 0; }
             if (pix_cur == 0xffffffffu) break;
             continue;
         }
@@ -213,7 +223,7 @@ __global__ void __launch_bounds__(GRT_MEGA_THREADS, GRT_MEGA_MIN_BLOCKS) render_
         mr.pixel = my_pixel_index; mr.sample = my_sample; mr.bounce = (uint32_t)bounce; mr.k0 = P.k0; mr.k1 = P.k1; mr.count = 0;
         HitInfo h;
         const float INF = __int_as_float(0x7f800000);
-        bool hit = closest_hit<FEAT, false, STATS>(sv, P.scene.root, ray, 0.001f, INF, self_id, &mr, h, &tc);   // camera.go:300
+        bool hit = closest_hit<FEAT, false, STATS>(sv, P.scene.root, ray, 0.001f, INF, self_id, self_ref, &mr, h, &tc);   // camera.go:300
 
         f3 Lterm = mk3(0, 0, 0);
         bool terminate = false, isnan_path = false;
@@ -247,6 +257,7 @@ __global__ void __launch_bounds__(GRT_MEGA_THREADS, GRT_MEGA_MIN_BLOCKS) render_
                     else {
                         ray_setup<FEAT>(ray, s.p, R.dir, ray.time);
                         self_id = s.is_surface ? s.id : GRT_NO_ID;
+                        self_ref = s.is_surface ? h.ref : 0xFFFFFFFFu;
                     }
                 }
             }
@@ -331,6 +342,14 @@ static uint32_t scan_features(const GrtScene* s) {
         if (s->lights[i].type == GRT_LIGHT_TRI) f |= F_TRI_LIGHT;
     }
     if (s->tri_shade) f |= F_TRISHADE;
+    {   // does any object id name more than one flat primitive (an object listed or instanced twice)?
+        std::vector<uint32_t> ids;
+        for (uint32_t i = 0; i < s->n_spheres; i++) ids.push_back(s->spheres[i].id);
+        for (uint32_t i = 0; i < s->n_quads; i++) ids.push_back(s->quads[i].id);
+        for (uint32_t i = 0; i < s->n_tris; i++) ids.push_back(s->tris[i].id);
+        std::sort(ids.begin(), ids.end());
+        for (size_t i = 1; i < ids.size(); i++) if (ids[i] == ids[i - 1]) { f |= F_DUPIDS; break; }
+    }
     return f;
 }
 
@@ -413,7 +432,8 @@ extern "C" int grt_scene_upload(const GrtScene* s, int device, GrtSceneHandle* o
     auto place = [&](uint32_t bytes) { uint32_t o = off; off = align16(off + bytes); return o; };
     ds.off_nodes = place(s->n_nodes * (uint32_t)sizeof(GrtNode));
     ds.off_spheres = place(s->n_spheres * (uint32_t)sizeof(GrtSphere));
-    ds.off_quads = place(s->n_quads * (uint32_t)sizeof(GrtQuad));
+    ds.off_quads = place(s->n_quads * (uint32_t)sizeof(DQuadHot));
+    ds.off_quads_cold = place(s->n_quads * (uint32_t)sizeof(DQuadCold));
     // run-length list entries (device-internal): consecutive items of one primitive type with
     // consecutive indices collapse into {first ref, count}; LIST refs are remapped to entry indices
     std::vector<uint32_t> item2entry(s->n_items + 1, 0);
@@ -458,7 +478,32 @@ extern "C" int grt_scene_upload(const GrtScene* s, int device, GrtSceneHandle* o
     auto put = [&](uint32_t o, const void* p, size_t bytes) { if (bytes) memcpy(blob.data() + o, p, bytes); };
     put(ds.off_nodes, nodes.data(), s->n_nodes * sizeof(GrtNode));
     put(ds.off_spheres, s->spheres, s->n_spheres * sizeof(GrtSphere));
-    put(ds.off_quads, s->quads, s->n_quads * sizeof(GrtQuad));
+    {
+        std::vector<DQuadHot> hot(s->n_quads);
+        std::vector<DQuadCold> cold(s->n_quads);
+        for (uint32_t i = 0; i < s->n_quads; i++) {
+            const GrtQuad& q = s->quads[i];
+            hot[i].plane = make_float4(q.n[0], q.n[1], q.n[2], q.D);
+            double aq = (double)q.A[0] * q.Q[0] + (double)q.A[1] * q.Q[1] + (double)q.A[2] * q.Q[2];
+            double bq = (double)q.B[0] * q.Q[0] + (double)q.B[1] * q.Q[1] + (double)q.B[2] * q.Q[2];
+            hot[i].A = make_float4(q.A[0], q.A[1], q.A[2], (float)-aq);
+            hot[i].B = make_float4(q.B[0], q.B[1], q.B[2], (float)-bq);
+            DQuadCold& c = cold[i];
+            memset(&c, 0, sizeof(c));
+            // NewONB(normal), onb.go:13-25, in fp64
+            double n[3] = {q.n64[0], q.n64[1], q.n64[2]};
+            double a[3] = {fabs(n[0]) > 0.9 ? 0.0 : 1.0, fabs(n[0]) > 0.9 ? 1.0 : 0.0, 0.0};
+            double v[3] = {n[1] * a[2] - n[2] * a[1], n[2] * a[0] - n[0] * a[2], n[0] * a[1] - n[1] * a[0]};
+            double vl = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+            for (int k = 0; k < 3; k++) v[k] /= vl;
+            double u[3] = {n[1] * v[2] - n[2] * v[1], n[2] * v[0] - n[0] * v[2], n[0] * v[1] - n[1] * v[0]};
+            double ul = sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+            for (int k = 0; k < 3; k++) { u[k] /= ul; c.n[k] = q.n[k]; c.ou[k] = (float)u[k]; c.ov[k] = (float)v[k]; c.n64[k] = q.n64[k]; }
+            c.flags = q.flags; c.mat = q.mat; c.id = q.id; c.D64 = q.D64;
+        }
+        put(ds.off_quads, hot.data(), hot.size() * sizeof(DQuadHot));
+        put(ds.off_quads_cold, cold.data(), cold.size() * sizeof(DQuadCold));
+    }
     put(ds.off_items, entries.data(), n_entries * 8u);
     put(ds.off_media, media.data(), s->n_media * sizeof(GrtMedium));
     put(ds.off_materials, s->materials, s->n_materials * sizeof(GrtMaterial));
@@ -517,6 +562,7 @@ unsigned int* grt_internal_counter(GrtSceneHandle h) { return h->d_counter; }
 #define V_SPHERES (F_NODE | F_SPHERE | F_LIST | F_SPECULAR | F_TEXTURE | F_SPHERE_LIGHT | F_DEFOCUS)
 #define V_MESH (F_NODE | F_SPHERE | F_TRI | F_LIST | F_SPECULAR | F_SPHERE_LIGHT | F_TRI_LIGHT | F_TRISHADE | F_DEFOCUS)
 #define V_FULL F_ALL
+#define V_NODUP(v) ((v) & ~F_DUPIDS)
 
 template <uint32_t FEAT>
 static int launch_trace(GrtSceneDev* h, const GrtRay* d_rays, uint64_t n, GrtHit* d_hits, cudaStream_t st) {
@@ -537,7 +583,7 @@ extern "C" int grt_trace_batch_device(GrtSceneHandle h, const GrtRay* d_rays, ui
     if (n == 0) return GRT_OK;
     CUDA_TRY(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
-    uint32_t f = h->ds.features;
+    uint32_t f = h->ds.features & ~F_DUPIDS;   // the trace kernels always exclude by object id
     if ((f & ~V_CORNELL) == 0) return launch_trace<V_CORNELL>(h, d_rays, n, d_hits, st);
     if ((f & ~V_SMOKE) == 0) return launch_trace<V_SMOKE>(h, d_rays, n, d_hits, st);
     if ((f & ~V_SPHERES) == 0) return launch_trace<V_SPHERES>(h, d_rays, n, d_hits, st);
@@ -569,6 +615,7 @@ extern "C" int grt_trace_batch(GrtSceneHandle h, const GrtRay* rays, uint64_t n,
 int grt_make_dev_camera(const GrtCamera* c, DevCamera* out) {
     if (!c) { grt_set_error("camera is NULL"); return GRT_E_INVALID; }
     if (c->width <= 0 || c->height <= 0 || c->spp_sqrt <= 0 || c->max_depth < 0) { grt_set_error("camera: width/height/spp_sqrt must be positive"); return GRT_E_INVALID; }
+    if (c->width > 65535 || c->height > 65535) { grt_set_error("camera: image larger than 65535 pixels on a side"); return GRT_E_UNSUPPORTED; }
     if (c->max_depth + 1 > WEIGHT_STACK) { grt_set_error("camera: MaxDepth exceeds the kernel's weight stack (63)"); return GRT_E_UNSUPPORTED; }
     if ((uint64_t)c->spp_sqrt * (uint64_t)c->spp_sqrt > 0xffffffffull) { grt_set_error("camera: more than 2^32 strata per pixel"); return GRT_E_UNSUPPORTED; }
     DevCamera d;
