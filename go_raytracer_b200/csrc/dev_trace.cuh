@@ -151,6 +151,14 @@ __device__ __forceinline__ bool sphere_hit(const GrtSphere& s, const RayD& r, fl
     return true;
 }
 
+// One MUFU.RCP (1 ulp) and a multiply; __fdividef adds ~5 range-scaling instructions we do not need
+// (a denominator below 1e-8 is rejected anyway).
+__device__ __forceinline__ float fast_div(float x, float y) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(y));
+    return x * r;
+}
+
 // ---- quad.Hit + isInterior, objects.go:167-206 -----------------------------
 // Branch-free fp32 candidate test on the 48-byte hot record.  For a quad that
 // is not axis-aligned the fp32 plane distance D - n.o loses relative accuracy
@@ -161,7 +169,7 @@ __device__ __forceinline__ bool quad_hit(const DQuadHot* q, const RayD& r, float
     const float4 P = q->plane, A = q->A, B = q->B;
     const float denom = P.x * r.d.x + P.y * r.d.y + P.z * r.d.z;
     const float num = P.w - (P.x * r.o.x + P.y * r.o.y + P.z * r.o.z);
-    const float t = __fdividef(num, denom);        // 2 ulp, far inside the 1e-5 budget
+    const float t = fast_div(num, denom);          // 2 ulp, far inside the 1e-5 budget
     const float px = fmaf(t, r.d.x, r.o.x), py = fmaf(t, r.d.y, r.o.y), pz = fmaf(t, r.d.z, r.o.z);
     const float alpha = fmaf(A.x, px, fmaf(A.y, py, fmaf(A.z, pz, A.w)));
     const float beta = fmaf(B.x, px, fmaf(B.y, py, fmaf(B.z, pz, B.w)));
@@ -224,7 +232,7 @@ __device__ bool closest_hit(const SceneView& sv, uint32_t root, const RayD& r, f
     uint32_t stack[STACK];
     int sp = 0;
     stack[sp++] = root;
-    bool any = false;
+    hit.ref = GRT_MAKE_REF(GRT_REF_NONE, 0);   // "no hit yet"; the closest t lives in tmax
     const float4* nodes = sv.nodes();
     const uint32_t excl = BOUNDARY ? GRT_NO_ID : self_id;
     const uint32_t excl_ref = BOUNDARY ? 0xFFFFFFFFu : self_ref;
@@ -242,7 +250,7 @@ __device__ bool closest_hit(const SceneView& sv, uint32_t root, const RayD& r, f
                 // a planar primitive cannot be re-hit by a ray leaving it (the fp64 reference finds t ~ 1e-13 < tmin)
                 if (FEAT & F_DUPIDS) ok = ok && (sv.quads_cold()[idx + k].id != excl);
                 else ok = ok & ((ref + k) != excl_ref);
-                if (ok) { any = true; tmax = t; hit.t = t; hit.ref = ref + k; hit.u = a; hit.v = b; }
+                if (ok) { tmax = t; hit.ref = ref + k; hit.u = a; hit.v = b; }
             }
             return true;
         }
@@ -251,7 +259,7 @@ __device__ bool closest_hit(const SceneView& sv, uint32_t root, const RayD& r, f
             if (STATS) tc->sphere += n;
             for (uint32_t k = 0; k < n; k++, s++) {
                 float t;
-                if (sphere_hit(*s, r, tmin, tmax, s->id == excl, t)) { any = true; tmax = t; hit.t = t; hit.ref = ref + k; hit.u = 0; hit.v = 0; }
+                if (sphere_hit(*s, r, tmin, tmax, s->id == excl, t)) { tmax = t; hit.ref = ref + k; hit.u = 0; hit.v = 0; }
             }
             return true;
         }
@@ -259,7 +267,7 @@ __device__ bool closest_hit(const SceneView& sv, uint32_t root, const RayD& r, f
             if (STATS) tc->tri += n;
             for (uint32_t k = 0; k < n; k++) {
                 float t, u, v;
-                if (tri_hit(sv.ds->tris + idx + k, r, tmin, tmax, excl, t, u, v)) { any = true; tmax = t; hit.t = t; hit.ref = ref + k; hit.u = u; hit.v = v; }
+                if (tri_hit(sv.ds->tris + idx + k, r, tmin, tmax, excl, t, u, v)) { tmax = t; hit.ref = ref + k; hit.u = u; hit.v = v; }
             }
             return true;
         }
@@ -316,11 +324,13 @@ __device__ bool closest_hit(const SceneView& sv, uint32_t root, const RayD& r, f
             float hitDistance = m.neg_inv_density * logf(u);
             if (hitDistance > inside) continue;
             float t = t1 + hitDistance / rayLength;
-            any = true; tmax = t; hit.t = t; hit.ref = ref; hit.u = 0; hit.v = 0;
+            tmax = t; hit.ref = ref; hit.u = 0; hit.v = 0;
             continue;
         }
         test_prims(ref, 1);   // a primitive that is a direct BVH child (bvh.go:73,79), or NONE
     }
+    const bool any = hit.ref != GRT_MAKE_REF(GRT_REF_NONE, 0);
+    hit.t = tmax;
     if ((FEAT & F_ROTQUAD) && any && GRT_REF_TYPE(hit.ref) == GRT_REF_QUAD) hit.t = quad_refine_t(sv.quads_cold() + (hit.ref & GRT_REF_MASK), r, hit.t);
     return any;
 }

@@ -5,9 +5,11 @@
 #include "../../include/grt.h"
 
 #define GRT_MEGA_THREADS 128
-#define GRT_MEGA_MIN_BLOCKS 4
+#ifndef GRT_MEGA_MIN_BLOCKS
+#define GRT_MEGA_MIN_BLOCKS 5   /* 96 registers, 20 warps/SM: measured best of 4/5/6 (profiles/) */
+#endif
 // the scene blob is staged into shared memory when every resident block can hold a copy
-#define GRT_STAGE_MAX_BYTES (48u * 1024u)
+#define GRT_STAGE_MAX_BYTES (40u * 1024u)
 
 namespace grtd { struct DevScene; struct DevCamera; }
 

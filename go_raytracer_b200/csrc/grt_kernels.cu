@@ -102,6 +102,16 @@ struct RenderParams {
 
 #define WEIGHT_STACK 64
 
+// T *= w, except that exactly-zero components are recorded in zinfo instead (see render_mega_kernel)
+__device__ __forceinline__ void apply_factor(f3& T, uint32_t& zinfo, f3 w, int sp_after) {
+    if (w.x == 0.0f | w.y == 0.0f | w.z == 0.0f) {
+        if (w.x == 0.0f) { zinfo = (zinfo & ~0x000000ffu) | (uint32_t)sp_after | (1u << 24); w.x = 1.0f; }
+        if (w.y == 0.0f) { zinfo = (zinfo & ~0x0000ff00u) | ((uint32_t)sp_after << 8) | (1u << 25); w.y = 1.0f; }
+        if (w.z == 0.0f) { zinfo = (zinfo & ~0x00ff0000u) | ((uint32_t)sp_after << 16) | (1u << 26); w.z = 1.0f; }
+    }
+    T = T * w;
+}
+
 template <uint32_t FEAT, bool STAGED, bool STATS>
 __global__ void __launch_bounds__(GRT_MEGA_THREADS, GRT_MEGA_MIN_BLOCKS) render_mega_kernel(const __grid_constant__ RenderParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -152,9 +162,19 @@ __global__ void __launch_bounds__(GRT_MEGA_THREADS, GRT_MEGA_MIN_BLOCKS) render_
     RayD ray;
     uint32_t self_id = GRT_NO_ID, self_ref = 0xFFFFFFFFu, my_sample = 0, my_pixel_index = 0;
     int bounce = 0;
-    f3 head = mk3(1, 1, 1), wtop = mk3(0, 0, 0);
+    // Recursive firefly clamp (camera.go:327-341) without recursion.  With T = running product of all
+    // weights/attenuations, E = terminal radiance and P0 = T (x) E, the radiance returned at clamped
+    // vertex j is P_j * S_j with P_j = P0 / T_before_j (componentwise) and
+    // S_j = min(S_{j+1}, M / sum(P_j)); hence L0 = P0 * min(1, M / max_j dot(P0, 1/T_before_j)).
+    // The stack keeps R_j = 1/T_before_j per clamped vertex; the unwind is one dot product and a max
+    // per entry (no dependent divide/compare chain).  An exactly-zero factor component (e.g. gold's
+    // blue albedo, main.go:382) cannot be divided out again, so zero factors are kept OUT of T and
+    // tracked in zinfo: byte c = number of stack entries whose suffix contains a zero in component c,
+    // bit 24+c = a zero was seen at all (then the final component is 0).
+    f3 T = mk3(1, 1, 1);
+    uint32_t zinfo = 0;
     int sp = 0;
-    f3 wstack[WEIGHT_STACK];
+    f3 rstack[WEIGHT_STACK];
     // stats
     uint32_t st_paths = 0, st_segments = 0, st_diffuse = 0, st_specular = 0, st_lightpdf = 0, st_nan = 0;
     TraceCounters tc;
@@ -178,7 +198,7 @@ __global__ void __launch_bounds__(GRT_MEGA_THREADS, GRT_MEGA_MIN_BLOCKS) render_
                 f3 o, d; float time;
                 camera_ray<FEAT>(cam, px, py, my_sample, my_pixel_index, P.k0, P.k1, o, d, time);
                 ray_setup<FEAT>(ray, o, d, time);
-                self_id = GRT_NO_ID; self_ref = 0xFFFFFFFFu; bounce = 0; head = mk3(1, 1, 1); sp = 0;
+                self_id = GRT_NO_ID; self_ref = 0xFFFFFFFFu; bounce = 0; T = mk3(1, 1, 1); zinfo = 0; sp = 0;
                 active = true;
                 if (STATS) st_paths++;
             }
@@ -194,8 +214,7 @@ __global__ void __launch_bounds__(GRT_MEGA_THREADS, GRT_MEGA_MIN_BLOCKS) render_
         }
         // ---- retire pix_cur once no lane works on it and its strata are all handed out
         bool cur_done_alloc = alloc_on_nxt || (k_alloc >= P.n_my);
-        unsigned on_cur = __ballot_sync(FULL, active && my_parity == 0u);
-        if (cur_done_alloc && on_cur == 0u) {
+        if (cur_done_alloc && __ballot_sync(FULL, active && my_parity == 0u) == 0u) {
             f3 s = acc0;
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {
@@ -240,15 +259,16 @@ __global__ void __launch_bounds__(GRT_MEGA_THREADS, GRT_MEGA_MIN_BLOCKS) render_
             if (R.kind == SHADE_TERMINATE) { Lterm = R.value; terminate = true; }
             else if (R.kind == SHADE_NAN) { isnan_path = true; terminate = true; }
             else {
-                if (R.kind == SHADE_SPECULAR) {   // camera.go:315-317: unclamped, folds into the parent weight
+                if (R.kind == SHADE_SPECULAR) {   // camera.go:315-317: unclamped, folds into the product
                     if (STATS) st_specular++;
-                    if (sp > 0) wtop = wtop * R.value; else head = head * R.value;
+                    apply_factor(T, zinfo, R.value, sp);
                 } else {                          // camera.go:319-330: a clamped vertex
                     if (STATS) st_diffuse++;
                     if (R.value.x == 0.0f && R.value.y == 0.0f && R.value.z == 0.0f) { terminate = true; }  // weight 0: the sample is 0 whatever follows
                     else {
-                        if (sp > 0) wstack[sp - 1] = wtop;
-                        wtop = R.value; sp++;
+                        // 1/T_before_j; a zero component stays zero in P0 as well, so its reciprocal is irrelevant
+                        rstack[sp++] = mk3(fminf(__frcp_rn(T.x), 1e30f), fminf(__frcp_rn(T.y), 1e30f), fminf(__frcp_rn(T.z), 1e30f));
+                        apply_factor(T, zinfo, R.value, sp);
                     }
                 }
                 if (!terminate) {
@@ -267,11 +287,16 @@ __global__ void __launch_bounds__(GRT_MEGA_THREADS, GRT_MEGA_MIN_BLOCKS) render_
             if (isnan_path) { L = mk3(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000), __int_as_float(0x7fc00000)); if (STATS) st_nan++; }
             else if (L.x != 0.0f || L.y != 0.0f || L.z != 0.0f) {
                 // unwind the recursion of camera.go:327-330 from the terminal radiance
-                if (sp > 0) {
-                    L = clamp_contribution(wtop * L, cam.max_contribution);
-                    for (int i = sp - 2; i >= 0; i--) L = clamp_contribution(wstack[i] * L, cam.max_contribution);
+                L = T * L;                                    // P0 without the zero factors
+                float worst = 0.0f;                           // max_j sum(P_j)
+                const int zx = (int)(zinfo & 255u), zy = (int)((zinfo >> 8) & 255u), zz = (int)((zinfo >> 16) & 255u);
+                for (int i = 0; i < sp; i++) {
+                    f3 rj = rstack[i];
+                    float sj = (i >= zx ? L.x * rj.x : 0.0f) + (i >= zy ? L.y * rj.y : 0.0f) + (i >= zz ? L.z * rj.z : 0.0f);
+                    worst = fmaxf(worst, sj);
                 }
-                L = head * L;
+                if (worst > cam.max_contribution) L = L * __fdividef(cam.max_contribution, worst);
+                if (zinfo >> 24) { if (zinfo & (1u << 24)) L.x = 0.0f; if (zinfo & (1u << 25)) L.y = 0.0f; if (zinfo & (1u << 26)) L.z = 0.0f; }
             }
             if (my_parity == 0u) acc0 = acc0 + L; else acc1 = acc1 + L;
             active = false;
