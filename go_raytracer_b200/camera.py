@@ -16,10 +16,10 @@ def derive_camera(cfg):
 class DeviceScene:
     """A flattened scene resident in HBM on one device."""
 
-    def __init__(self, scene, device=0):
+    def __init__(self, scene, device=0, collapse_whole=None, collapse_leaf=None):
         self._L = N.lib()
         self.scene = scene
-        flat = scene.flatten()
+        flat = scene.flatten(collapse_whole, collapse_leaf)
         h = C.c_void_p()
         N.check(self._L.grt_scene_upload(C.byref(flat), int(device), C.byref(h)))
         self._h = h

@@ -115,9 +115,15 @@ int grt_host_builtin_scene(GrtHostScene* s, int scene_id, const GrtSceneOptions*
 }
 
 int grt_host_flatten(GrtHostScene* s, GrtScene* out) {
+    grt::flat::FlattenOptions o;
+    return grt_host_flatten_opts(s, o.collapse_whole, o.collapse_leaf, out);
+}
+int grt_host_flatten_opts(GrtHostScene* s, int collapse_whole, int collapse_leaf, GrtScene* out) {
     if (!s || !out) return fail("NULL argument");
     s->flat.reset(new grt::flat::FlatScene());
-    grt::flat::Flattener f(s->ir);
+    grt::flat::FlattenOptions fo;
+    fo.collapse_whole = collapse_whole; fo.collapse_leaf = collapse_leaf;
+    grt::flat::Flattener f(s->ir, fo);
     if (!f.run(*s->flat)) { s->flat.reset(); return fail(f.error); }
     *out = s->flat->view();
     return 0;

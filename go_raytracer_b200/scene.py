@@ -143,10 +143,14 @@ class Scene:
         self.lights = obj
 
     # ---- flatten / description ---------------------------------------------------
-    def flatten(self):
-        """hittable.Flatten: returns the GrtScene view (valid while this Scene lives)."""
+    def flatten(self, collapse_whole=None, collapse_leaf=None):
+        """hittable.Flatten: returns the GrtScene view (valid while this Scene lives, until the next flatten).
+        collapse_* tune how much of each BVH is emitted as ordered leaf runs (results do not depend on them)."""
         s = N.GrtScene()
-        N.host_check(self._L.grt_host_flatten(self._h, C.byref(s)))
+        if collapse_whole is None and collapse_leaf is None:
+            N.host_check(self._L.grt_host_flatten(self._h, C.byref(s)))
+        else:
+            N.host_check(self._L.grt_host_flatten_opts(self._h, int(collapse_whole or 0), int(collapse_leaf or 0), C.byref(s)))
         return s
 
     def description_ptr(self):

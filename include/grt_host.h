@@ -75,6 +75,11 @@ int grt_host_builtin_scene(GrtHostScene* s, int scene_id, const GrtSceneOptions*
 /* hittable.Flatten: BuildBVH + bake + flatten.  *out points into storage owned by s
  * (valid until the next flatten or grt_host_scene_free). */
 int grt_host_flatten(GrtHostScene* s, GrtScene* out);
+/* Same with explicit tuning: a BuildBVH result with <= collapse_whole leaves, and inside larger trees any
+ * subtree with <= collapse_leaf leaves, is emitted as an ordered run of its leaves (visiting order of
+ * bvh.go:69-82) instead of nodes.  (0, 0) reproduces the reference's tree node for node.  Closest-hit
+ * results do not depend on these values. */
+int grt_host_flatten_opts(GrtHostScene* s, int collapse_whole, int collapse_leaf, GrtScene* out);
 /* Camera.initialize (camera.go:179-253). */
 int grt_host_camera_derive(const GrtCameraConfig* cfg, GrtCamera* out);
 /* P3 text exactly as camera.go:160 + color.go:45 write it; returns bytes written or -1. */
