@@ -70,7 +70,7 @@ class GrtScene(C.Structure):
                 ("spheres", C.c_void_p), ("n_spheres", C.c_uint32),
                 ("quads", C.c_void_p), ("n_quads", C.c_uint32),
                 ("tris", C.c_void_p), ("n_tris", C.c_uint32),
-                ("tri_shade", C.c_void_p),
+                ("tri_shade", C.c_void_p), ("tri_v64", C.c_void_p),
                 ("items", C.c_void_p), ("n_items", C.c_uint32),
                 ("media", C.c_void_p), ("n_media", C.c_uint32),
                 ("materials", C.c_void_p), ("n_materials", C.c_uint32),

@@ -19,7 +19,12 @@ enum : uint32_t {
     F_SPHERE_LIGHT = 1u << 9, F_QUAD_LIGHT = 1u << 10, F_TRI_LIGHT = 1u << 11, F_TRISHADE = 1u << 12,
     F_DEFOCUS = 1u << 13, F_NODE = 1u << 14,
     F_DUPIDS = 1u << 15,   // some object id names more than one flat primitive: exclude by id, not by flat ref
-    F_ALL = (1u << 16) - 1
+    F_ALL = (1u << 16) - 1,
+    // not a scene feature: the C-ABI ray query accepts rays that start ON a plane without naming it, so its
+    // t >= tmin decisions fall back to the fp64 plane when the origin is within fp32 resolution of that plane.
+    // The integrator always names the primitive it starts on (self exclusion), which leaves such events at
+    // ~1e-7 per segment, and compiles the fallback out of its quad loop.
+    F_TMIN_F64 = 1u << 16
 };
 #define GRT_NEEDS_F64(FEAT) (((FEAT) & F_SPHERE) != 0)
 
@@ -45,6 +50,7 @@ struct DevScene {
     uint32_t n_nodes, n_spheres, n_quads, n_items, n_media, n_materials, n_textures, n_lights, n_images;
     const GrtTri* tris;          // HBM
     const GrtTriShade* tri_shade;
+    const double* tri_v64;
     const uint8_t* texels;
     const GrtPerlin* perlins;
     uint32_t n_tris, n_perlins;
@@ -165,7 +171,9 @@ __device__ __forceinline__ float fast_div(float x, float y) {
 // when the origin is close to the plane; the WINNING hit is therefore refined
 // in fp64 by quad_refine_t (one refinement per segment instead of fp64
 // arithmetic in every test).
-__device__ __forceinline__ bool quad_hit(const DQuadHot* q, const RayD& r, float tmin, float tmax, float& t_out, float& a_out, float& b_out) {
+// `uncertain` is set when the plane distance at tmin, D - n.(o + tmin d), is within fp32 rounding of zero (the
+// origin lies almost on this plane): the accept/reject decision t >= tmin then needs the fp64 plane.
+__device__ __forceinline__ bool quad_hit(const DQuadHot* q, const RayD& r, float tmin, float tmax, float& t_out, float& a_out, float& b_out, bool& uncertain) {
     const float4 P = q->plane, A = q->A, B = q->B;
     const float denom = P.x * r.d.x + P.y * r.d.y + P.z * r.d.z;
     const float num = P.w - (P.x * r.o.x + P.y * r.o.y + P.z * r.o.z);
@@ -176,7 +184,24 @@ __device__ __forceinline__ bool quad_hit(const DQuadHot* q, const RayD& r, float
     const bool ok = (fabsf(denom) >= 1e-8f) & (tmin <= t) & (t <= tmax)            // objects.go:171,177 (closed interval)
                     & (0.0f <= alpha) & (alpha <= 1.0f) & (0.0f <= beta) & (beta <= 1.0f);   // objects.go:199
     t_out = t; a_out = alpha; b_out = beta;
+    uncertain = fabsf(fmaf(-tmin, denom, num)) < 2.5e-4f;
     return ok;
+}
+// The same test with the fp64 plane (rare path: origin within fp32 resolution of the plane).
+__device__ __forceinline__ bool quad_hit_f64(const DQuadHot* q, const DQuadCold* c, const RayD& r, float tmin, float tmax, float& t_out, float& a_out, float& b_out) {
+    const double denom = c->n64[0] * (double)r.d.x + c->n64[1] * (double)r.d.y + c->n64[2] * (double)r.d.z;
+    if (fabs(denom) < 1e-8) return false;
+    const double num = c->D64 - (c->n64[0] * (double)r.o.x + c->n64[1] * (double)r.o.y + c->n64[2] * (double)r.o.z);
+    const double t64 = num / denom;
+    if (!((double)tmin <= t64 && t64 <= (double)tmax)) return false;
+    const float t = (float)t64;
+    const float4 A = q->A, B = q->B;
+    const float px = fmaf(t, r.d.x, r.o.x), py = fmaf(t, r.d.y, r.o.y), pz = fmaf(t, r.d.z, r.o.z);
+    const float alpha = fmaf(A.x, px, fmaf(A.y, py, fmaf(A.z, pz, A.w)));
+    const float beta = fmaf(B.x, px, fmaf(B.y, py, fmaf(B.z, pz, B.w)));
+    if (!((0.0f <= alpha) & (alpha <= 1.0f) & (0.0f <= beta) & (beta <= 1.0f))) return false;
+    t_out = t; a_out = alpha; b_out = beta;
+    return true;
 }
 __device__ __forceinline__ float quad_refine_t(const DQuadCold* q, const RayD& r, float t32) {
     if (q->flags & GRT_QUAD_AXIS_ALIGNED) return t32;   // D - n.o and n.d are single-rounding there
@@ -206,6 +231,17 @@ __device__ __forceinline__ bool tri_hit(const GrtTri* tp, const RayD& r, float t
     if (tl < tmin || tl > tmax) return false;
     t_out = tl; u_out = u; v_out = v;
     return true;
+}
+
+// t of the winning triangle recomputed in fp64 from the fp64 vertices (same expression order as objects.go:409-433).
+__device__ __forceinline__ float tri_refine_t(const double* v, const RayD& r, float t32) {
+    const d3 v0 = ldd3(v), e0 = ldd3(v + 3) - v0, e1 = ldd3(v + 6) - v0;
+    const d3 o = tod3(r.o), d = tod3(r.d);
+    const d3 pvec = cross(d, e1);
+    const double det = dot(e0, pvec);
+    if (fabs(det) < 1e-300) return t32;
+    const d3 qvec = cross(o - v0, e0);
+    return (float)(dot(e1, qvec) / det);
 }
 
 #define GRT_STACK_MAIN 48
@@ -246,7 +282,9 @@ __device__ bool closest_hit(const SceneView& sv, uint32_t root, const RayD& r, f
 #pragma unroll 2
             for (uint32_t k = 0; k < n; k++) {
                 float t, a, b;
-                bool ok = quad_hit(q + k, r, tmin, tmax, t, a, b);
+                bool unc;
+                bool ok = quad_hit(q + k, r, tmin, tmax, t, a, b, unc);
+                if ((FEAT & F_TMIN_F64) && (FEAT & F_ROTQUAD) && unc) ok = quad_hit_f64(q + k, sv.quads_cold() + idx + k, r, tmin, tmax, t, a, b);
                 // a planar primitive cannot be re-hit by a ray leaving it (the fp64 reference finds t ~ 1e-13 < tmin)
                 if (FEAT & F_DUPIDS) ok = ok && (sv.quads_cold()[idx + k].id != excl);
                 else ok = ok & ((ref + k) != excl_ref);
@@ -332,6 +370,7 @@ __device__ bool closest_hit(const SceneView& sv, uint32_t root, const RayD& r, f
     const bool any = hit.ref != GRT_MAKE_REF(GRT_REF_NONE, 0);
     hit.t = tmax;
     if ((FEAT & F_ROTQUAD) && any && GRT_REF_TYPE(hit.ref) == GRT_REF_QUAD) hit.t = quad_refine_t(sv.quads_cold() + (hit.ref & GRT_REF_MASK), r, hit.t);
+    if ((FEAT & F_TRI) && any && GRT_REF_TYPE(hit.ref) == GRT_REF_TRI && sv.ds->tri_v64) hit.t = tri_refine_t(sv.ds->tri_v64 + 9 * (size_t)(hit.ref & GRT_REF_MASK), r, hit.t);
     return any;
 }
 

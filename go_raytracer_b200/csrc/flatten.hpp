@@ -77,6 +77,7 @@ struct FlatScene {
     std::vector<GrtQuad> quads;
     std::vector<GrtTri> tris;
     std::vector<GrtTriShade> tri_shade;
+    std::vector<double> tri_v64;
     std::vector<uint32_t> items;
     std::vector<GrtMedium> media;
     std::vector<GrtMaterial> materials;
@@ -98,6 +99,7 @@ struct FlatScene {
         s.quads = quads.data(); s.n_quads = (uint32_t)quads.size();
         s.tris = tris.data(); s.n_tris = (uint32_t)tris.size();
         s.tri_shade = any_tri_shade ? tri_shade.data() : nullptr;
+        s.tri_v64 = tri_v64.empty() ? nullptr : tri_v64.data();
         s.items = items.data(); s.n_items = (uint32_t)items.size();
         s.media = media.data(); s.n_media = (uint32_t)media.size();
         s.materials = materials.data(); s.n_materials = (uint32_t)materials.size();
@@ -458,6 +460,7 @@ class Flattener {
                 if (g.flags) F->any_tri_shade = true;
                 F->tris.push_back(g);
                 F->tri_shade.push_back(sh);
+                { const V3* vv[3] = {&v0, &v1, &v2}; for (int k = 0; k < 3; k++) { F->tri_v64.push_back(vv[k]->x); F->tri_v64.push_back(vv[k]->y); F->tri_v64.push_back(vv[k]->z); } }
                 e.ref = GRT_MAKE_REF(GRT_REF_TRI, F->tris.size() - 1);
                 e.box.add(v0); e.box.add(v1); e.box.add(v2);
                 break;

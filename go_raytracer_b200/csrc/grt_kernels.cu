@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(128) trace_batch_kernel(const __grid_constant_
     mr.pixel = (uint32_t)i; mr.sample = (uint32_t)(i >> 32); mr.bounce = 0; mr.k0 = 0; mr.k1 = 0; mr.count = 0;
     HitInfo h;
     GrtHit out;
-    if (closest_hit<FEAT | F_DUPIDS, false, false>(sv, ds.root, r, a.w, b.w, self_id, 0xFFFFFFFFu, &mr, h, nullptr)) {
+    if (closest_hit<FEAT | F_DUPIDS | F_TMIN_F64, false, false>(sv, ds.root, r, a.w, b.w, self_id, 0xFFFFFFFFu, &mr, h, nullptr)) {
         Surface s;
         finish_hit<FEAT>(sv, r, h, true, s);
         out.t = h.t; out.id = s.id; out.ref = h.ref; out.front_face = s.front ? 1u : 0u;
@@ -337,6 +337,7 @@ struct GrtSceneDev {
     void* d_blob = nullptr;
     void* d_tris = nullptr;
     void* d_tri_shade = nullptr;
+    void* d_tri_v64 = nullptr;
     void* d_texels = nullptr;
     void* d_perlins = nullptr;
     unsigned int* d_counter = nullptr;
@@ -551,11 +552,13 @@ extern "C" int grt_scene_upload(const GrtScene* s, int device, GrtSceneHandle* o
     if ((rc = upload(&h->d_blob, blob.data(), blob.size()))) { grt_scene_free(h); return rc; }
     if ((rc = upload(&h->d_tris, s->tris, (size_t)s->n_tris * sizeof(GrtTri)))) { grt_scene_free(h); return rc; }
     if (s->tri_shade && (rc = upload(&h->d_tri_shade, s->tri_shade, (size_t)s->n_tris * sizeof(GrtTriShade)))) { grt_scene_free(h); return rc; }
+    if (s->tri_v64 && (rc = upload(&h->d_tri_v64, s->tri_v64, (size_t)s->n_tris * 9 * sizeof(double)))) { grt_scene_free(h); return rc; }
     if ((rc = upload(&h->d_texels, s->texels, (size_t)s->n_texel_bytes))) { grt_scene_free(h); return rc; }
     if ((rc = upload(&h->d_perlins, s->perlins, (size_t)s->n_perlins * sizeof(GrtPerlin)))) { grt_scene_free(h); return rc; }
     ds.blob = (const unsigned char*)h->d_blob;
     ds.tris = (const GrtTri*)h->d_tris;
     ds.tri_shade = (const GrtTriShade*)h->d_tri_shade;
+    ds.tri_v64 = (const double*)h->d_tri_v64;
     ds.texels = (const uint8_t*)h->d_texels;
     ds.perlins = (const GrtPerlin*)h->d_perlins;
     CUDA_TRY(cudaMalloc((void**)&h->d_counter, 256));
@@ -570,7 +573,7 @@ extern "C" int grt_scene_upload(const GrtScene* s, int device, GrtSceneHandle* o
 extern "C" int grt_scene_free(GrtSceneHandle h) {
     if (!h) return GRT_OK;
     cudaSetDevice(h->device);
-    cudaFree(h->d_blob); cudaFree(h->d_tris); cudaFree(h->d_tri_shade); cudaFree(h->d_texels); cudaFree(h->d_perlins); cudaFree(h->d_counter);
+    cudaFree(h->d_blob); cudaFree(h->d_tris); cudaFree(h->d_tri_shade); cudaFree(h->d_tri_v64); cudaFree(h->d_texels); cudaFree(h->d_perlins); cudaFree(h->d_counter);
     delete h;
     return GRT_OK;
 }

@@ -190,6 +190,9 @@ typedef struct GrtScene {
     const GrtQuad*     quads;      uint32_t n_quads;
     const GrtTri*      tris;       uint32_t n_tris;
     const GrtTriShade* tri_shade;  /* n_tris entries, or NULL if no tri has normals/uv */
+    const double*      tri_v64;    /* n_tris x 9 doubles (v0,v1,v2), or NULL: fp64 vertices used to refine the
+                                      WINNING triangle's t (fp32 Moller-Trumbore loses relative accuracy when the
+                                      origin is almost coplanar, e.g. a ray leaving a neighbouring mesh triangle) */
     const uint32_t*    items;      uint32_t n_items;   /* HittableList items: child refs in list order, GRT_LIST_LAST on each list's last */
     const GrtMedium*   media;      uint32_t n_media;
     const GrtMaterial* materials;  uint32_t n_materials;
