@@ -267,7 +267,7 @@ def run_ours(args):
         if world == 1 and not args.no_cpu:
             from oracle import oracle_py as O
             cores = os.cpu_count() or 1
-            sb, cfgb = g.builtin_scene(6, width=args.width, spp=args.ref_spp)
+            sb, cfgb = g.builtin_scene(6, width=args.width, spp=args.cpu_spp)
             ow = O.OracleWorld(sb)
             camb = O.derived_camera(cfgb)
             _, _, _, sec = ow.render(cfgb, nthreads=cores)
@@ -298,7 +298,8 @@ def main():
     ap.add_argument("--variant", default="mega", choices=["mega", "wavefront"])
     ap.add_argument("--width", type=int, default=1024)
     ap.add_argument("--spp", type=int, default=4096)
-    ap.add_argument("--ref-spp", type=int, default=16, help="spp of the bounded CPU sample")
+    ap.add_argument("--ref-spp", type=int, default=64, help="--impl reference: spp of each step's bounded sample")
+    ap.add_argument("--cpu-spp", type=int, default=256, help="spp of the cpu_baseline sample (about 10-30 s of CPU work)")
     ap.add_argument("--seed", type=int, default=0xC0FFEE)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -181,8 +181,11 @@ __device__ __forceinline__ bool quad_hit(const DQuadHot* q, const RayD& r, float
     const float px = fmaf(t, r.d.x, r.o.x), py = fmaf(t, r.d.y, r.o.y), pz = fmaf(t, r.d.z, r.o.z);
     const float alpha = fmaf(A.x, px, fmaf(A.y, py, fmaf(A.z, pz, A.w)));
     const float beta = fmaf(B.x, px, fmaf(B.y, py, fmaf(B.z, pz, B.w)));
+    // 0 <= x <= 1  <=>  x - x*x >= 0 (one FMA, exact in sign; closed like objects.go:199).  Moves four compares
+    // from the ALU pipe (the busiest pipe of this loop, profiles/r1_mega_v4) to the FMA pipe.
+    const float ia = fmaf(-alpha, alpha, alpha), ib = fmaf(-beta, beta, beta);
     const bool ok = (fabsf(denom) >= 1e-8f) & (tmin <= t) & (t <= tmax)            // objects.go:171,177 (closed interval)
-                    & (0.0f <= alpha) & (alpha <= 1.0f) & (0.0f <= beta) & (beta <= 1.0f);   // objects.go:199
+                    & (fminf(ia, ib) >= 0.0f) & (alpha == alpha) & (beta == beta);
     t_out = t; a_out = alpha; b_out = beta;
     uncertain = fabsf(fmaf(-tmin, denom, num)) < 2.5e-4f;
     return ok;
