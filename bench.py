@@ -236,7 +236,7 @@ def run_ours(args):
         s2, cfg2 = g.builtin_scene(6, width=args.width, spp=16)
         cam2 = g.derive_camera(cfg2)
         sc2 = g.DeviceScene(s2, local)
-        _, _, st = sc2.render(cam2, seed=args.seed, variant=variant, want_stats=True)
+        _, _, st = sc2.render(cam2, seed=args.seed, variant=N.GRT_VARIANT_MEGAKERNEL, want_stats=True)   # event counts are variant-independent
         sc2.close()
         flops_pp, bytes_pp = algorithmic_cost(st)
         bytes_pp += 12.0 / S2                                       # fp32 RGB write per pixel, amortised

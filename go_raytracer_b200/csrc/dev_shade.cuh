@@ -407,4 +407,38 @@ __device__ __forceinline__ f3 clamp_contribution(f3 c, float maxValue) {  // cam
     return c;
 }
 
+// ---- recursive firefly clamp (camera.go:327-341) without recursion -------------------------
+// See DESIGN.md §3.2.  T = running product of the non-zero weight components, zinfo tracks
+// exactly-zero components, rstack[j] = 1/T_before_j for each clamped vertex.
+#define WEIGHT_STACK 64
+
+// T *= w, except that exactly-zero components are recorded in zinfo instead: byte c = number of stack
+// entries whose suffix contains a zero in component c, bit 24+c = a zero was seen at all.
+__device__ __forceinline__ void apply_factor(f3& T, uint32_t& zinfo, f3 w, int sp_after) {
+    if (w.x == 0.0f | w.y == 0.0f | w.z == 0.0f) {
+        if (w.x == 0.0f) { zinfo = (zinfo & ~0x000000ffu) | (uint32_t)sp_after | (1u << 24); w.x = 1.0f; }
+        if (w.y == 0.0f) { zinfo = (zinfo & ~0x0000ff00u) | ((uint32_t)sp_after << 8) | (1u << 25); w.y = 1.0f; }
+        if (w.z == 0.0f) { zinfo = (zinfo & ~0x00ff0000u) | ((uint32_t)sp_after << 16) | (1u << 26); w.z = 1.0f; }
+    }
+    T = T * w;
+}
+__device__ __forceinline__ f3 recip_factor(f3 T) { return mk3(fminf(__frcp_rn(T.x), 1e30f), fminf(__frcp_rn(T.y), 1e30f), fminf(__frcp_rn(T.z), 1e30f)); }
+
+// L0 = P0 * min(1, M / max_j sum(P_j)),  P0 = T (x) E,  sum(P_j) = P0 . rstack[j] over the components whose
+// suffix from j holds no zero factor.  `stride` lets the wavefront variant keep the stack depth-major in HBM.
+template <class StackPtr>
+__device__ __forceinline__ f3 unwind_clamp(f3 T, uint32_t zinfo, f3 E, StackPtr rstack, int sp, float max_contribution, size_t stride = 1) {
+    f3 L = T * E;
+    float worst = 0.0f;
+    const int zx = (int)(zinfo & 255u), zy = (int)((zinfo >> 8) & 255u), zz = (int)((zinfo >> 16) & 255u);
+    for (int i = 0; i < sp; i++) {
+        const auto rj = rstack[(size_t)i * stride];
+        float sj = (i >= zx ? L.x * rj.x : 0.0f) + (i >= zy ? L.y * rj.y : 0.0f) + (i >= zz ? L.z * rj.z : 0.0f);
+        worst = fmaxf(worst, sj);
+    }
+    if (worst > max_contribution) L = L * __fdividef(max_contribution, worst);
+    if (zinfo >> 24) { if (zinfo & (1u << 24)) L.x = 0.0f; if (zinfo & (1u << 25)) L.y = 0.0f; if (zinfo & (1u << 26)) L.z = 0.0f; }
+    return L;
+}
+
 }  // namespace grtd

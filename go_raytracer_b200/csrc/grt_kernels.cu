@@ -100,18 +100,6 @@ struct RenderParams {
     GrtStats* stats;
 };
 
-#define WEIGHT_STACK 64
-
-// T *= w, except that exactly-zero components are recorded in zinfo instead (see render_mega_kernel)
-__device__ __forceinline__ void apply_factor(f3& T, uint32_t& zinfo, f3 w, int sp_after) {
-    if (w.x == 0.0f | w.y == 0.0f | w.z == 0.0f) {
-        if (w.x == 0.0f) { zinfo = (zinfo & ~0x000000ffu) | (uint32_t)sp_after | (1u << 24); w.x = 1.0f; }
-        if (w.y == 0.0f) { zinfo = (zinfo & ~0x0000ff00u) | ((uint32_t)sp_after << 8) | (1u << 25); w.y = 1.0f; }
-        if (w.z == 0.0f) { zinfo = (zinfo & ~0x00ff0000u) | ((uint32_t)sp_after << 16) | (1u << 26); w.z = 1.0f; }
-    }
-    T = T * w;
-}
-
 template <uint32_t FEAT, bool STAGED, bool STATS>
 __global__ void __launch_bounds__(GRT_MEGA_THREADS, GRT_MEGA_MIN_BLOCKS) render_mega_kernel(const __grid_constant__ RenderParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -287,16 +275,7 @@ __global__ void __launch_bounds__(GRT_MEGA_THREADS, GRT_MEGA_MIN_BLOCKS) render_
             if (isnan_path) { L = mk3(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000), __int_as_float(0x7fc00000)); if (STATS) st_nan++; }
             else if (L.x != 0.0f || L.y != 0.0f || L.z != 0.0f) {
                 // unwind the recursion of camera.go:327-330 from the terminal radiance
-                L = T * L;                                    // P0 without the zero factors
-                float worst = 0.0f;                           // max_j sum(P_j)
-                const int zx = (int)(zinfo & 255u), zy = (int)((zinfo >> 8) & 255u), zz = (int)((zinfo >> 16) & 255u);
-                for (int i = 0; i < sp; i++) {
-                    f3 rj = rstack[i];
-                    float sj = (i >= zx ? L.x * rj.x : 0.0f) + (i >= zy ? L.y * rj.y : 0.0f) + (i >= zz ? L.z * rj.z : 0.0f);
-                    worst = fmaxf(worst, sj);
-                }
-                if (worst > cam.max_contribution) L = L * __fdividef(cam.max_contribution, worst);
-                if (zinfo >> 24) { if (zinfo & (1u << 24)) L.x = 0.0f; if (zinfo & (1u << 25)) L.y = 0.0f; if (zinfo & (1u << 26)) L.z = 0.0f; }
+                L = unwind_clamp(T, zinfo, L, rstack, sp, cam.max_contribution);
             }
             if (my_parity == 0u) acc0 = acc0 + L; else acc1 = acc1 + L;
             active = false;

@@ -1,7 +1,319 @@
-// grt_wavefront.cu — wavefront variant (placeholder until implemented).
+// grt_wavefront.cu — the wavefront variant of the render loop (GRT_VARIANT_WAVEFRONT).
+//
+// Same arithmetic and the same Philox streams as the megakernel (dev_trace.cuh / dev_shade.cuh),
+// different execution shape: a pool of path slots lives in HBM and every bounce is a sequence of
+// coherent kernels
+//
+//   wf_generate   free slots take the next (pixel, stratum) and a camera ray       camera.go:256-290
+//   wf_extend     closest hit for every live slot; the slot index is appended to    bvh.go:69, hittable.go:122
+//                 the queue of its material class with a warp ballot/popc compaction
+//   wf_shade<Q>   one launch per queue: TERMINAL (miss / light: unwind + accumulate), camera.go:301-314
+//                 DIFFUSE (Lambertian / Isotropic: PDF mixture), SPECULAR            camera.go:315-330
+//
+// so that shading never runs with a partially filled warp.  The price is moving ~100 bytes of path
+// state through HBM per segment and one atomicAdd per finished path (paths of one pixel are spread
+// over the pool), which also makes the fp32 sums order-dependent.  profiles/README.md compares the two
+// variants with ncu counters.
+#include <cuda_runtime.h>
+#include <string.h>
+#include <stdlib.h>
+#include <string>
 #include "dev_shade.cuh"
 #include "grt_internal.h"
+
+using namespace grtd;
+
+#define WF_FREE 0xFFFFFFFFu
+enum { Q_TERMINAL = 0, Q_DIFFUSE = 1, Q_SPECULAR = 2, Q_COUNT = 3 };
+// counters[]: 0..2 queue sizes, 3 live slots after extend, 4 finished flag scratch
+enum { C_LIVE = 3, C_WORDS = 8 };
+
+struct WfParams {
+    DevScene scene;
+    DevCamera cam;
+    uint32_t k0, k1;
+    uint32_t sample_first, sample_stride, n_my;
+    int x0, y0, ww, wh;
+    uint32_t n_pixels;
+    uint32_t P;                       // pool size (slots)
+    unsigned long long total;         // n_pixels * n_my
+    float4* S0;                       // o.xyz, time
+    float4* S1;                       // d.xyz, self_ref
+    float4* S2;                       // T.xyz, zinfo
+    uint4* S3;                        // pixel index, sample, bounce | sp << 8 (WF_FREE = empty), self_id
+    float4* H;                        // t, ref, u, v
+    float4* rstack;                   // [WEIGHT_STACK][P], depth-major
+    uint32_t* queues;                 // [Q_COUNT][P]
+    uint32_t* counters;               // C_WORDS
+    unsigned long long* next_sample;
+    float* rgb_sum;
+};
+
+__device__ __forceinline__ SceneView wf_view(const WfParams& P, unsigned char* smem, bool staged) {
+    SceneView sv;
+    sv.ds = &P.scene;
+    if (staged) { stage_blob(smem, P.scene); sv.base = smem; }
+    else sv.base = P.scene.blob;
+    return sv;
+}
+
+// ---- generate ----------------------------------------------------------------------------------
+template <uint32_t FEAT>
+__global__ void __launch_bounds__(256) wf_generate(const __grid_constant__ WfParams P) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned FULL = 0xffffffffu;
+    bool want = slot < P.P && P.S3[slot].z == WF_FREE;
+    // warp-aggregated claim of sample indices
+    unsigned mask = __ballot_sync(FULL, want);
+    if (!mask) return;
+    const uint32_t lane = threadIdx.x & 31u;
+    unsigned long long base = 0;
+    if (lane == (uint32_t)(__ffs(mask) - 1)) base = atomicAdd(P.next_sample, (unsigned long long)__popc(mask));
+    base = __shfl_sync(FULL, base, __ffs(mask) - 1);
+    if (!want) return;
+    unsigned long long idx = base + __popc(mask & ((1u << lane) - 1u));
+    if (idx >= P.total) return;
+    // stratum-major order: consecutive slots get consecutive pixels of one stratum (coherent camera rays)
+    uint32_t k = (uint32_t)(idx / P.n_pixels), q = (uint32_t)(idx - (unsigned long long)k * P.n_pixels);
+    uint32_t row = q / (uint32_t)P.ww;
+    int px = P.x0 + (int)(q - row * (uint32_t)P.ww), py = P.y0 + (int)row;
+    uint32_t sample = P.sample_first + k * P.sample_stride;
+    uint32_t pixel_index = (uint32_t)(py * P.cam.width + px);
+    f3 o, d; float time;
+    camera_ray<FEAT>(P.cam, px, py, sample, pixel_index, P.k0, P.k1, o, d, time);
+    P.S0[slot] = make_float4(o.x, o.y, o.z, time);
+    P.S1[slot] = make_float4(d.x, d.y, d.z, __uint_as_float(0xFFFFFFFFu));
+    P.S2[slot] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(0u));
+    P.S3[slot] = make_uint4(pixel_index, sample, 0u, GRT_NO_ID);
+}
+
+// ---- extend + enqueue ----------------------------------------------------------------------------
+template <uint32_t FEAT, bool STAGED>
+__global__ void __launch_bounds__(256) wf_extend(const __grid_constant__ WfParams P) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    SceneView sv = wf_view(P, smem, STAGED);
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned FULL = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31u;
+    int q = -1;
+    if (slot < P.P) {
+        const uint4 s3 = P.S3[slot];
+        if (s3.z != WF_FREE) {
+            const float4 s0 = P.S0[slot], s1 = P.S1[slot];
+            RayD ray;
+            ray_setup<FEAT>(ray, mk3(s0.x, s0.y, s0.z), mk3(s1.x, s1.y, s1.z), s0.w);
+            MediumRngCtx mr;
+            mr.pixel = s3.x; mr.sample = s3.y; mr.bounce = s3.z & 255u; mr.k0 = P.k0; mr.k1 = P.k1; mr.count = 0;
+            HitInfo h;
+            const float INF = __int_as_float(0x7f800000);
+            bool hit = closest_hit<FEAT, false, false>(sv, P.scene.root, ray, 0.001f, INF, s3.w, __float_as_uint(s1.w), &mr, h, nullptr);
+            if (!hit) { h.t = INF; h.ref = GRT_MAKE_REF(GRT_REF_NONE, 0); h.u = h.v = 0; q = Q_TERMINAL; }
+            else {
+                uint32_t type = GRT_REF_TYPE(h.ref), idx = h.ref & GRT_REF_MASK, mat;
+                if ((FEAT & F_QUAD) && type == GRT_REF_QUAD) mat = sv.quads_cold()[idx].mat;
+                else if ((FEAT & F_SPHERE) && type == GRT_REF_SPHERE) mat = sv.spheres()[idx].mat;
+                else if ((FEAT & F_TRI) && type == GRT_REF_TRI) mat = P.scene.tris[idx].mat;
+                else mat = sv.media()[idx].mat;
+                uint32_t mt = sv.materials()[mat].type;
+                q = (mt == GRT_MAT_DIFFUSE_LIGHT) ? Q_TERMINAL : ((mt == GRT_MAT_METAL || mt == GRT_MAT_DIELECTRIC) ? Q_SPECULAR : Q_DIFFUSE);
+            }
+            P.H[slot] = make_float4(h.t, __uint_as_float(h.ref), h.u, h.v);
+        }
+    }
+    // per-material queues, compacted with ballot/popc: one atomicAdd per warp per queue
+#pragma unroll
+    for (int k = 0; k < Q_COUNT; k++) {
+        unsigned m = __ballot_sync(FULL, q == k);
+        if (!m) continue;
+        uint32_t base = 0;
+        int leader = __ffs(m) - 1;
+        if ((int)lane == leader) base = atomicAdd(P.counters + k, (uint32_t)__popc(m));
+        base = __shfl_sync(FULL, base, leader);
+        if (q == k) P.queues[(size_t)k * P.P + base + __popc(m & ((1u << lane) - 1u))] = slot;
+    }
+    unsigned live = __ballot_sync(FULL, q >= 0);
+    if (live && lane == 0) atomicAdd(P.counters + C_LIVE, (uint32_t)__popc(live));
+}
+
+// ---- shade ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void wf_finish_path(const WfParams& P, uint32_t slot, uint32_t pixel_index, f3 L) {
+    if (L.x != 0.0f || L.y != 0.0f || L.z != 0.0f) {   // NaN != 0 is true: a NaN sample is accumulated (color.go:28-36)
+        float* dst = P.rgb_sum + (size_t)pixel_index * 3;
+        atomicAdd(dst, L.x); atomicAdd(dst + 1, L.y); atomicAdd(dst + 2, L.z);
+    }
+    P.S3[slot].z = WF_FREE;
+}
+
+template <uint32_t FEAT, bool STAGED, int Q>
+__global__ void __launch_bounds__(256) wf_shade(const __grid_constant__ WfParams P) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    SceneView sv = wf_view(P, smem, STAGED);
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= P.counters[Q]) return;
+    const uint32_t slot = P.queues[(size_t)Q * P.P + j];
+    const uint4 s3 = P.S3[slot];
+    const float4 s0 = P.S0[slot], s1 = P.S1[slot], s2 = P.S2[slot], hh = P.H[slot];
+    const uint32_t bounce = s3.z & 255u;
+    int sp = (int)(s3.z >> 8);
+    f3 T = mk3(s2.x, s2.y, s2.z);
+    uint32_t zinfo = __float_as_uint(s2.w);
+    const float4* rs = P.rstack + slot;
+    RayD ray;
+    ray_setup<FEAT>(ray, mk3(s0.x, s0.y, s0.z), mk3(s1.x, s1.y, s1.z), s0.w);
+    HitInfo h;
+    h.t = hh.x; h.ref = __float_as_uint(hh.y); h.u = hh.z; h.v = hh.w;
+
+    if (Q == Q_TERMINAL) {
+        f3 E;
+        if (GRT_REF_TYPE(h.ref) == GRT_REF_NONE) E = P.cam.background;          // camera.go:301
+        else {
+            Surface s;
+            finish_hit<FEAT>(sv, ray, h, false, s);
+            const GrtMaterial mat = sv.materials()[s.mat];
+            if ((FEAT & F_SPHERE) && (FEAT & F_TEXTURE) && GRT_REF_TYPE(h.ref) == GRT_REF_SPHERE && material_needs_uv<FEAT>(sv, mat))
+                sphere_uv(sv.spheres()[h.ref & GRT_REF_MASK], s);
+            E = s.front ? texture_value<FEAT>(sv, mat.tex, s.u, s.v, s.p) : mk3(0, 0, 0);   // materials.go:150-155
+        }
+        f3 L = mk3(0, 0, 0);
+        if (E.x != 0.0f || E.y != 0.0f || E.z != 0.0f) L = unwind_clamp(T, zinfo, E, rs, sp, P.cam.max_contribution, P.P);
+        wf_finish_path(P, slot, s3.x, L);
+        return;
+    }
+    Surface s;
+    finish_hit<FEAT>(sv, ray, h, false, s);
+    const GrtMaterial mat = sv.materials()[s.mat];
+    if ((FEAT & F_SPHERE) && (FEAT & F_TEXTURE) && GRT_REF_TYPE(h.ref) == GRT_REF_SPHERE && material_needs_uv<FEAT>(sv, mat))
+        sphere_uv(sv.spheres()[h.ref & GRT_REF_MASK], s);
+    ShadeResult R = shade_vertex<FEAT>(sv, ray, s, mat, s3.x, s3.y, bounce, P.k0, P.k1, nullptr);
+    if (R.kind == SHADE_NAN) { const float qn = __int_as_float(0x7fc00000); wf_finish_path(P, slot, s3.x, mk3(qn, qn, qn)); return; }
+    if (R.kind == SHADE_TERMINATE) {   // not reached for Q_DIFFUSE / Q_SPECULAR materials
+        wf_finish_path(P, slot, s3.x, mk3(0, 0, 0));
+        return;
+    }
+    if (R.kind == SHADE_SPECULAR) apply_factor(T, zinfo, R.value, sp);
+    else {
+        if (R.value.x == 0.0f && R.value.y == 0.0f && R.value.z == 0.0f) { wf_finish_path(P, slot, s3.x, mk3(0, 0, 0)); return; }
+        f3 r = recip_factor(T);
+        P.rstack[(size_t)sp * P.P + slot] = make_float4(r.x, r.y, r.z, 0.0f);
+        sp++;
+        apply_factor(T, zinfo, R.value, sp);
+    }
+    if ((int)bounce + 1 > P.cam.max_depth) { wf_finish_path(P, slot, s3.x, mk3(0, 0, 0)); return; }   // camera.go:294-296
+    P.S0[slot] = make_float4(s.p.x, s.p.y, s.p.z, s0.w);
+    P.S1[slot] = make_float4(R.dir.x, R.dir.y, R.dir.z, __uint_as_float(s.is_surface ? h.ref : 0xFFFFFFFFu));
+    P.S2[slot] = make_float4(T.x, T.y, T.z, __uint_as_float(zinfo));
+    P.S3[slot] = make_uint4(s3.x, s3.y, (bounce + 1u) | ((uint32_t)sp << 8), s.is_surface ? s.id : GRT_NO_ID);
+}
+
+__global__ void wf_init_slots(uint4* S3, uint32_t P) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < P) S3[i] = make_uint4(0, 0, WF_FREE, GRT_NO_ID);
+}
+
+// ---- host driver ---------------------------------------------------------------------------------------
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) { grt_set_error(std::string("wavefront: ") + #call + ": " + cudaGetErrorString(e_)); rc = GRT_E_CUDA; goto done; } \
+    } while (0)
+
+#define V_CORNELL (F_QUAD | F_LIST | F_ROTQUAD | F_QUAD_LIGHT)
+#define V_SMOKE (V_CORNELL | F_MEDIUM | F_ISOTROPIC)
+
+template <uint32_t FEAT>
+static int wf_run(GrtSceneHandle h, WfParams& P, cudaStream_t st, uint32_t* h_counters) {
+    int rc = GRT_OK;
+    const bool staged = grt_internal_staged(h);
+    const size_t smem = staged ? P.scene.blob_bytes : 0;
+    const unsigned blocks = (P.P + 255) / 256;
+    const bool has_spec = (P.scene.features & F_SPECULAR) != 0;
+    uint64_t launches = 0;
+    if (smem) {
+        cudaFuncSetAttribute(wf_extend<FEAT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(wf_shade<FEAT, true, Q_TERMINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(wf_shade<FEAT, true, Q_DIFFUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(wf_shade<FEAT, true, Q_SPECULAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    }
+    wf_init_slots<<<blocks, 256, 0, st>>>(P.S3, P.P);
+    launches++;
+    CU(cudaMemsetAsync(P.next_sample, 0, 8, st));
+    for (uint64_t iter = 0;; iter++) {
+        CU(cudaMemsetAsync(P.counters, 0, C_WORDS * 4, st));
+        wf_generate<FEAT><<<blocks, 256, 0, st>>>(P);
+        if (staged) {
+            wf_extend<FEAT, true><<<blocks, 256, smem, st>>>(P);
+            wf_shade<FEAT, true, Q_TERMINAL><<<blocks, 256, smem, st>>>(P);
+            wf_shade<FEAT, true, Q_DIFFUSE><<<blocks, 256, smem, st>>>(P);
+            if (has_spec) wf_shade<FEAT, true, Q_SPECULAR><<<blocks, 256, smem, st>>>(P);
+        } else {
+            wf_extend<FEAT, false><<<blocks, 256, 0, st>>>(P);
+            wf_shade<FEAT, false, Q_TERMINAL><<<blocks, 256, 0, st>>>(P);
+            wf_shade<FEAT, false, Q_DIFFUSE><<<blocks, 256, 0, st>>>(P);
+            if (has_spec) wf_shade<FEAT, false, Q_SPECULAR><<<blocks, 256, 0, st>>>(P);
+        }
+        launches += has_spec ? 5 : 4;
+        if ((iter & 7u) == 7u || iter < 2) {   // the host only needs to know when the pool has drained
+            CU(cudaMemcpyAsync(h_counters, P.counters, C_WORDS * 4, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            if (h_counters[C_LIVE] == 0) break;
+        }
+        if (iter > (1ull << 40)) { grt_set_error("wavefront: did not drain"); rc = GRT_E_CUDA; goto done; }
+    }
+    CU(cudaGetLastError());
+done:
+    grt_count_launch(launches);
+    return rc;
+}
+
 int grt_render_wavefront(GrtSceneHandle h, const GrtCamera* cam, const GrtOptions* opt, float* d_rgb_sum, cudaStream_t st, GrtStats* d_stats) {
-    grt_set_error("wavefront variant not built yet");
-    return GRT_E_UNSUPPORTED;
+    (void)d_stats;
+    int rc = GRT_OK;
+    WfParams P;
+    memset(&P, 0, sizeof(P));
+    if ((rc = grt_make_dev_camera(cam, &P.cam))) return rc;
+    P.scene = *grt_internal_dev_scene(h);
+    P.k0 = (uint32_t)opt->seed; P.k1 = (uint32_t)(opt->seed >> 32);
+    const uint32_t S2 = (uint32_t)cam->spp_sqrt * (uint32_t)cam->spp_sqrt;
+    const uint32_t stride = opt->sample_stride ? opt->sample_stride : 1u;
+    if (opt->sample_first >= S2) return GRT_OK;
+    P.sample_first = opt->sample_first; P.sample_stride = stride;
+    P.n_my = (S2 - opt->sample_first + stride - 1) / stride;
+    int x0 = opt->x0, y0 = opt->y0, x1 = opt->x1, y1 = opt->y1;
+    if (x0 == 0 && y0 == 0 && x1 == 0 && y1 == 0) { x1 = cam->width; y1 = cam->height; }
+    if (x0 < 0 || y0 < 0 || x1 > cam->width || y1 > cam->height || x1 <= x0 || y1 <= y0) { grt_set_error("GrtOptions pixel window out of range"); return GRT_E_INVALID; }
+    P.x0 = x0; P.y0 = y0; P.ww = x1 - x0; P.wh = y1 - y0;
+    P.n_pixels = (uint32_t)P.ww * (uint32_t)P.wh;
+    P.total = (unsigned long long)P.n_pixels * P.n_my;
+    unsigned long long pool_slots = 1ull << 21;   // 2 Mi slots: ~2.4 GB of state at full size
+    if (const char* e = getenv("GRT_WF_SLOTS")) { unsigned long long v = strtoull(e, nullptr, 10); if (v >= 256) pool_slots = v; }
+    unsigned long long want = P.total < pool_slots ? P.total : pool_slots;
+    P.P = (uint32_t)((want + 255) / 256 * 256);
+    P.rgb_sum = d_rgb_sum;
+    void* pool = nullptr;
+    uint32_t* h_counters = nullptr;
+    {
+        size_t n = P.P;
+        size_t bytes = n * 16 * 5 + n * 16 * (size_t)(cam->max_depth + 1) + n * 4 * Q_COUNT + C_WORDS * 4 + 64;
+        CU(cudaMalloc(&pool, bytes));
+        unsigned char* p = (unsigned char*)pool;
+        P.S0 = (float4*)p; p += n * 16; P.S1 = (float4*)p; p += n * 16; P.S2 = (float4*)p; p += n * 16;
+        P.S3 = (uint4*)p; p += n * 16; P.H = (float4*)p; p += n * 16;
+        P.rstack = (float4*)p; p += n * 16 * (size_t)(cam->max_depth + 1);
+        P.queues = (uint32_t*)p; p += n * 4 * Q_COUNT;
+        P.counters = (uint32_t*)p; p += C_WORDS * 4;
+        p = (unsigned char*)(((uintptr_t)p + 15) & ~(uintptr_t)15);
+        P.next_sample = (unsigned long long*)p;
+        CU(cudaMallocHost((void**)&h_counters, C_WORDS * 4));
+    }
+    {
+        uint32_t f = (P.scene.features & ~F_DUPIDS) | (cam->defocus_angle > 0 ? F_DEFOCUS : 0u);
+        bool dup = (P.scene.features & F_DUPIDS) != 0;
+        if (!dup && (f & ~V_CORNELL) == 0) rc = wf_run<V_CORNELL>(h, P, st, h_counters);
+        else if (!dup && (f & ~V_SMOKE) == 0) rc = wf_run<V_SMOKE>(h, P, st, h_counters);
+        else rc = wf_run<F_ALL>(h, P, st, h_counters);
+    }
+done:
+    if (pool) { cudaStreamSynchronize(st); cudaFree(pool); }
+    if (h_counters) cudaFreeHost(h_counters);
+    return rc;
 }
