@@ -17,7 +17,7 @@ GRT_VARIANT_MEGAKERNEL, GRT_VARIANT_WAVEFRONT = 0, 1
 GRT_OPT_STATS = 1
 GRT_NO_ID = 0xFFFFFFFF
 REF_SHIFT, REF_MASK = 28, 0x0FFFFFFF
-REF_NODE, REF_SPHERE, REF_QUAD, REF_TRI, REF_LIST, REF_MEDIUM, REF_NONE = 0, 1, 2, 3, 4, 5, 7
+REF_NODE, REF_SPHERE, REF_QUAD, REF_TRI, REF_LIST, REF_MEDIUM, REF_BOX, REF_NONE = 0, 1, 2, 3, 4, 5, 6, 7
 LIST_LAST = 0x80000000
 
 
@@ -69,6 +69,7 @@ class GrtScene(C.Structure):
                 ("nodes", C.c_void_p), ("n_nodes", C.c_uint32),
                 ("spheres", C.c_void_p), ("n_spheres", C.c_uint32),
                 ("quads", C.c_void_p), ("n_quads", C.c_uint32),
+                ("boxes", C.c_void_p), ("n_boxes", C.c_uint32),
                 ("tris", C.c_void_p), ("n_tris", C.c_uint32),
                 ("tri_shade", C.c_void_p), ("tri_v64", C.c_void_p),
                 ("items", C.c_void_p), ("n_items", C.c_uint32),
@@ -88,6 +89,8 @@ SPHERE_DTYPE = np.dtype([("c0", "<f8", 3), ("r", "<f8"), ("dc", "<f4", 3), ("mat
                          ("flags", "<u4"), ("uvrot", "<f4", 2)])
 QUAD_DTYPE = np.dtype([("n", "<f4", 3), ("D", "<f4"), ("Q", "<f4", 3), ("flags", "<u4"), ("A", "<f4", 3),
                        ("mat", "<u4"), ("B", "<f4", 3), ("id", "<u4"), ("n64", "<f8", 3), ("D64", "<f8")])
+BOX_DTYPE = np.dtype([("mn", "<f4", 3), ("first_quad", "<u4"), ("mx", "<f4", 3), ("flags", "<u4"), ("T", "<f4", 3),
+                      ("rc", "<f4"), ("rs", "<f4"), ("pad", "<f4", 3)])
 TRI_DTYPE = np.dtype([("v0", "<f4", 3), ("mat", "<u4"), ("e0", "<f4", 3), ("id", "<u4"), ("e1", "<f4", 3),
                       ("flags", "<u4")])
 RAY_DTYPE = np.dtype([("o", "<f4", 3), ("tmin", "<f4"), ("d", "<f4", 3), ("tmax", "<f4"), ("time", "<f4"),

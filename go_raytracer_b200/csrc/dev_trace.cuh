@@ -19,7 +19,8 @@ enum : uint32_t {
     F_SPHERE_LIGHT = 1u << 9, F_QUAD_LIGHT = 1u << 10, F_TRI_LIGHT = 1u << 11, F_TRISHADE = 1u << 12,
     F_DEFOCUS = 1u << 13, F_NODE = 1u << 14,
     F_DUPIDS = 1u << 15,   // some object id names more than one flat primitive: exclude by id, not by flat ref
-    F_ALL = (1u << 16) - 1,
+    F_BOX = 1u << 17,      // NewBox results tested as one slab test (GrtBox)
+    F_ALL = ((1u << 16) - 1) | F_BOX,
     // not a scene feature: the C-ABI ray query accepts rays that start ON a plane without naming it, so its
     // t >= tmin decisions fall back to the fp64 plane when the origin is within fp32 resolution of that plane.
     // The integrator always names the primitive it starts on (self exclusion), which leaves such events at
@@ -46,8 +47,8 @@ struct DQuadCold {
 struct DevScene {
     const unsigned char* blob;   // HBM copy of the blob
     uint32_t blob_bytes;
-    uint32_t off_nodes, off_spheres, off_quads, off_quads_cold, off_items, off_media, off_materials, off_textures, off_lights, off_images;
-    uint32_t n_nodes, n_spheres, n_quads, n_items, n_media, n_materials, n_textures, n_lights, n_images;
+    uint32_t off_nodes, off_spheres, off_quads, off_quads_cold, off_boxes, off_items, off_media, off_materials, off_textures, off_lights, off_images;
+    uint32_t n_nodes, n_spheres, n_quads, n_boxes, n_items, n_media, n_materials, n_textures, n_lights, n_images;
     const GrtTri* tris;          // HBM
     const GrtTriShade* tri_shade;
     const double* tri_v64;
@@ -65,6 +66,7 @@ struct SceneView {
     __device__ __forceinline__ const GrtSphere* spheres() const { return (const GrtSphere*)(base + ds->off_spheres); }
     __device__ __forceinline__ const DQuadHot* quads() const { return (const DQuadHot*)(base + ds->off_quads); }
     __device__ __forceinline__ const DQuadCold* quads_cold() const { return (const DQuadCold*)(base + ds->off_quads_cold); }
+    __device__ __forceinline__ const GrtBox* boxes() const { return (const GrtBox*)(base + ds->off_boxes); }
     // run-length list entries built at upload: x = first ref (| GRT_LIST_LAST), y = number of consecutive primitives
     __device__ __forceinline__ const uint2* entries() const { return (const uint2*)(base + ds->off_items); }
     __device__ __forceinline__ const GrtMedium* media() const { return (const GrtMedium*)(base + ds->off_media); }
@@ -213,6 +215,45 @@ __device__ __forceinline__ float quad_refine_t(const DQuadCold* q, const RayD& r
     return __fdividef((float)num, (float)denom);
 }
 
+// ---- NewBox as one primitive (objects.go:208-240) ------------------------------
+// The six quads of a box are found with one slab test in the box's own frame (the ray is taken
+// to object space exactly as translate.Hit / rotateY.Hit do, transformation.go:25-34,94-107).
+// A line meets a convex box in at most two points, t_enter <= t_exit, each on one face; quad.Hit
+// over the six faces returns the smaller one that lies in [tmin, tmax] (closed, objects.go:177).
+// Returns the face index in NewBox's order (front, right, back, left, top, bottom) or -1.
+// `excl_face`: face of THIS box the ray starts on (-1 if none).  `near_tmin` reports a candidate
+// within fp32 resolution of tmin (see F_TMIN_F64).
+__device__ __forceinline__ int box_prim_hit(const GrtBox* bx, const RayD& r, float tmin, float tmax, int excl_face, float& t_out, bool& near_tmin) {
+    const float4 b0 = *(const float4*)&bx->mn[0], b1 = *(const float4*)&bx->mx[0], b2 = *(const float4*)&bx->T[0];
+    const float rs = bx->rs, rc = b2.w;
+    const float px = r.o.x - b2.x, py = r.o.y - b2.y, pz = r.o.z - b2.z;
+    const float ox = rc * px - rs * pz, oz = rs * px + rc * pz;          // rayTranslationHelper, transformation.go:79-85
+    const float dx = rc * r.d.x - rs * r.d.z, dz = rs * r.d.x + rc * r.d.z, dy = r.d.y;
+    float ix, iy, iz;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ix) : "f"(dx));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iy) : "f"(dy));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iz) : "f"(dz));
+    const float ax = (b0.x - ox) * ix, bx_ = (b1.x - ox) * ix;
+    const float ay = (b0.y - py) * iy, by = (b1.y - py) * iy;
+    const float az = (b0.z - oz) * iz, bz = (b1.z - oz) * iz;
+    const float lox = fminf(ax, bx_), hix = fmaxf(ax, bx_);
+    const float loy = fminf(ay, by), hiy = fmaxf(ay, by);
+    const float loz = fminf(az, bz), hiz = fmaxf(az, bz);
+    const float t_enter = fmaxf(fmaxf(lox, loy), loz), t_exit = fminf(fminf(hix, hiy), hiz);
+    near_tmin = false;
+    if (!(t_enter <= t_exit)) return -1;
+    // faces: 0 front z=max, 1 right x=max, 2 back z=min, 3 left x=min, 4 top y=max, 5 bottom y=min
+    // entering through axis a: the min face when d_a > 0, else the max face; leaving: the other way round
+    int f_enter, f_exit;
+    float d_enter, d_exit;
+    if (lox >= loy && lox >= loz) { f_enter = dx > 0 ? 3 : 1; d_enter = dx; } else if (loy >= loz) { f_enter = dy > 0 ? 5 : 4; d_enter = dy; } else { f_enter = dz > 0 ? 2 : 0; d_enter = dz; }
+    if (hix <= hiy && hix <= hiz) { f_exit = dx > 0 ? 1 : 3; d_exit = dx; } else if (hiy <= hiz) { f_exit = dy > 0 ? 4 : 5; d_exit = dy; } else { f_exit = dz > 0 ? 0 : 2; d_exit = dz; }
+    near_tmin = (fabsf((t_enter - tmin) * d_enter) < 2.5e-4f) | (fabsf((t_exit - tmin) * d_exit) < 2.5e-4f);
+    if (tmin <= t_enter && t_enter <= tmax && f_enter != excl_face) { t_out = t_enter; return f_enter; }
+    if (tmin <= t_exit && t_exit <= tmax && f_exit != excl_face) { t_out = t_exit; return f_exit; }
+    return -1;
+}
+
 // ---- Triangle.Hit (Möller–Trumbore), objects.go:408-461 --------------------
 __device__ __forceinline__ bool tri_hit(const GrtTri* tp, const RayD& r, float tmin, float tmax, uint32_t self_id, float& t_out, float& u_out, float& v_out) {
     const float4 a = __ldg((const float4*)tp);        // v0, mat
@@ -295,6 +336,29 @@ __device__ bool closest_hit(const SceneView& sv, uint32_t root, const RayD& r, f
             }
             return true;
         }
+        if ((FEAT & F_BOX) && type == GRT_REF_BOX) {
+            const GrtBox* bx = sv.boxes() + idx;
+            if (STATS) tc->box += n;
+            for (uint32_t k = 0; k < n; k++, bx++) {
+                const uint32_t qref = GRT_MAKE_REF(GRT_REF_QUAD, bx->first_quad);
+                int excl_face = -1;
+                if (FEAT & F_DUPIDS) { for (int f = 0; f < 6; f++) if (sv.quads_cold()[bx->first_quad + f].id == excl) excl_face = f; }
+                else if (excl_ref - qref < 6u) excl_face = (int)(excl_ref - qref);
+                float t; bool near;
+                int face = box_prim_hit(bx, r, tmin, tmax, excl_face, t, near);
+                if ((FEAT & F_TMIN_F64) && near) {
+                    // a candidate within fp32 resolution of tmin: decide with the six quads (fp64 plane fallback inside)
+                    const DQuadHot* q = sv.quads() + bx->first_quad;
+                    for (int f = 0; f < 6; f++) {
+                        float tq, a, b; bool unc;
+                        bool ok = quad_hit(q + f, r, tmin, tmax, tq, a, b, unc);
+                        if (unc) ok = quad_hit_f64(q + f, sv.quads_cold() + bx->first_quad + f, r, tmin, tmax, tq, a, b);
+                        if (ok && f != excl_face) { tmax = tq; hit.ref = qref + f; hit.u = a; hit.v = b; }
+                    }
+                } else if (face >= 0) { tmax = t; hit.ref = qref + (uint32_t)face; hit.u = 0; hit.v = 0; }
+            }
+            return true;
+        }
         if ((FEAT & F_SPHERE) && type == GRT_REF_SPHERE) {
             const GrtSphere* s = sv.spheres() + idx;
             if (STATS) tc->sphere += n;
@@ -312,7 +376,7 @@ __device__ bool closest_hit(const SceneView& sv, uint32_t root, const RayD& r, f
             }
             return true;
         }
-        return type == GRT_REF_QUAD || type == GRT_REF_SPHERE || type == GRT_REF_TRI || type == GRT_REF_NONE;
+        return type == GRT_REF_QUAD || type == GRT_REF_SPHERE || type == GRT_REF_TRI || type == GRT_REF_BOX || type == GRT_REF_NONE;
     };
 
     while (sp > 0) {
@@ -418,6 +482,11 @@ __device__ __forceinline__ void finish_hit(const SceneView& sv, const RayD& r, c
         s.mat = __float_as_uint(c1.w); s.id = __float_as_uint(c2.w);
         set_face_normal(s, r.d, mk3(c0.x, c0.y, c0.z));
         s.has_onb = true; s.ou = mk3(c1.x, c1.y, c1.z); s.ov = mk3(c2.x, c2.y, c2.z);
+        if ((FEAT & F_BOX) && (FEAT & (F_TEXTURE | F_TMIN_F64))) {   // a box hit carries no (alpha, beta): recompute them (objects.go:187-188)
+            const float4 A = sv.quads()[idx].A, B = sv.quads()[idx].B;
+            s.u = fmaf(A.x, s.p.x, fmaf(A.y, s.p.y, fmaf(A.z, s.p.z, A.w)));
+            s.v = fmaf(B.x, s.p.x, fmaf(B.y, s.p.y, fmaf(B.z, s.p.z, B.w)));
+        }
         return;
     }
     if ((FEAT & F_SPHERE) && type == GRT_REF_SPHERE) {

@@ -75,6 +75,7 @@ struct FlatScene {
     std::vector<GrtNode> nodes;
     std::vector<GrtSphere> spheres;
     std::vector<GrtQuad> quads;
+    std::vector<GrtBox> boxes;
     std::vector<GrtTri> tris;
     std::vector<GrtTriShade> tri_shade;
     std::vector<double> tri_v64;
@@ -97,6 +98,7 @@ struct FlatScene {
         s.nodes = nodes.data(); s.n_nodes = (uint32_t)nodes.size();
         s.spheres = spheres.data(); s.n_spheres = (uint32_t)spheres.size();
         s.quads = quads.data(); s.n_quads = (uint32_t)quads.size();
+        s.boxes = boxes.data(); s.n_boxes = (uint32_t)boxes.size();
         s.tris = tris.data(); s.n_tris = (uint32_t)tris.size();
         s.tri_shade = any_tri_shade ? tri_shade.data() : nullptr;
         s.tri_v64 = tri_v64.empty() ? nullptr : tri_v64.data();
@@ -122,6 +124,7 @@ struct FlatScene {
 struct FlattenOptions {
     int collapse_whole = 32;   // a BuildBVH result with at most this many leaves becomes one list
     int collapse_leaf = 4;     // inside larger trees, subtrees with at most this many leaves become lists
+    bool box_prims = true;     // NewBox results are found with one slab test (GrtBox) instead of six quad tests
 };
 
 class Flattener {
@@ -159,6 +162,11 @@ class Flattener {
     struct BuildNode { int left, right; bool leftIsNode, rightIsNode; int leaves; };  // child: build-node index or hittable id
     struct Topology { std::vector<BuildNode> nodes; int root = -1; };
 
+    bool isBoxPrim(int listPayload) const {
+        if (!opt.box_prims || S.box_of_list[listPayload] < 0) return false;
+        const ir::BoxP& b = S.boxes[S.box_of_list[listPayload]];
+        return b.mx.x > b.mn.x && b.mx.y > b.mn.y && b.mx.z > b.mn.z;   // a flat "box" keeps its six quads
+    }
     // number of primitive tests a linear run over this hittable would make (-1: not collapsible)
     int leafCount(int hid) {
         const ir::Hittable& h = S.hittables[hid];
@@ -167,7 +175,8 @@ class Flattener {
             case ir::H_MEDIUM: return 1;   // stays a single ref inside a run
             case ir::H_TRANSLATE: case ir::H_ROTATEY: return leafCount(h.child);
             case ir::H_LIST: { int n = 0; for (int c : S.lists[h.a]) { int k = leafCount(c); n += k; if (n > (1 << 20)) return 1 << 20; } return n; }
-            case ir::H_BVH: return topology(h.a).nodes[topology(h.a).root].leaves;
+            case ir::H_BVH: if (isBoxPrim(h.a)) return 1;
+                return topology(h.a).nodes[topology(h.a).root].leaves;
         }
         return 1;
     }
@@ -343,7 +352,7 @@ class Flattener {
         bool leafOnly = true;
         for (size_t i = 0; i < refs.size(); i++) {
             uint32_t t = GRT_REF_TYPE(refs[i]);
-            if (t != GRT_REF_SPHERE && t != GRT_REF_QUAD && t != GRT_REF_TRI) leafOnly = false;
+            if (t != GRT_REF_SPHERE && t != GRT_REF_QUAD && t != GRT_REF_TRI && t != GRT_REF_BOX) leafOnly = false;
             F->items.push_back(refs[i] | (i + 1 == refs.size() ? GRT_LIST_LAST : 0u));
         }
         e.ref = GRT_MAKE_REF(GRT_REF_LIST, first);
@@ -470,6 +479,23 @@ class Flattener {
                 break;
             }
             case ir::H_BVH: {
+                if (isBoxPrim(h.a)) {
+                    // NewBox: emit its six quads contiguously in the reference's order, plus the slab record
+                    const ir::BoxP& bp = S.boxes[S.box_of_list[h.a]];
+                    uint32_t first = (uint32_t)F->quads.size();
+                    for (int i = 0; i < 6; i++) { Emitted q = emit(bp.quads[i], X, inBoundary); e.box.add(q.box); }
+                    GrtBox b;
+                    memset(&b, 0, sizeof(b));
+                    b.mn[0] = (float)bp.mn.x; b.mn[1] = (float)bp.mn.y; b.mn[2] = (float)bp.mn.z;
+                    b.mx[0] = (float)bp.mx.x; b.mx[1] = (float)bp.mx.y; b.mx[2] = (float)bp.mx.z;
+                    b.first_quad = first;
+                    b.T[0] = (float)X.T.x; b.T[1] = (float)X.T.y; b.T[2] = (float)X.T.z;
+                    b.rc = (float)X.c; b.rs = (float)X.s;
+                    F->boxes.push_back(b);
+                    e.ref = GRT_MAKE_REF(GRT_REF_BOX, F->boxes.size() - 1);
+                    e.need = 0;
+                    break;
+                }
                 const Topology& T = topology(h.a);
                 e = emitTopo(T, T.root, X, inBoundary);
                 break;

@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(128) trace_batch_kernel(const __grid_constant_
     GrtHit out;
     if (closest_hit<FEAT | F_DUPIDS | F_TMIN_F64, false, false>(sv, ds.root, r, a.w, b.w, self_id, 0xFFFFFFFFu, &mr, h, nullptr)) {
         Surface s;
-        finish_hit<FEAT>(sv, r, h, true, s);
+        finish_hit<FEAT | F_TMIN_F64>(sv, r, h, true, s);
         out.t = h.t; out.id = s.id; out.ref = h.ref; out.front_face = s.front ? 1u : 0u;
         out.p[0] = s.p.x; out.p[1] = s.p.y; out.p[2] = s.p.z; out.u = s.u;
         out.n[0] = s.n.x; out.n[1] = s.n.y; out.n[2] = s.n.z; out.v = s.v;
@@ -331,6 +331,7 @@ static uint32_t scan_features(const GrtScene* s) {
     if (s->n_nodes) f |= F_NODE;
     if (s->n_spheres) f |= F_SPHERE;
     if (s->n_quads) f |= F_QUAD;
+    if (s->n_boxes) f |= F_BOX;
     if (s->n_tris) f |= F_TRI;
     if (s->n_items) f |= F_LIST;
     if (s->n_media) f |= F_MEDIUM;
@@ -367,6 +368,7 @@ static int validate_scene(const GrtScene* s) {
             case GRT_REF_NODE: return i < s->n_nodes;
             case GRT_REF_SPHERE: return i < s->n_spheres;
             case GRT_REF_QUAD: return i < s->n_quads;
+            case GRT_REF_BOX: return i < s->n_boxes;
             case GRT_REF_TRI: return i < s->n_tris;
             case GRT_REF_LIST: return i < s->n_items;
             case GRT_REF_MEDIUM: return i < s->n_media;
@@ -384,6 +386,7 @@ static int validate_scene(const GrtScene* s) {
         if (!check_ref(s->media[i].boundary) || s->media[i].mat >= s->n_materials) { grt_set_error("medium ref out of range"); return GRT_E_INVALID; }
     }
     for (uint32_t i = 0; i < s->n_spheres; i++) if (s->spheres[i].mat >= s->n_materials) { grt_set_error("sphere material out of range"); return GRT_E_INVALID; }
+    for (uint32_t i = 0; i < s->n_boxes; i++) if ((uint64_t)s->boxes[i].first_quad + 6 > s->n_quads) { grt_set_error("box quad range out of range"); return GRT_E_INVALID; }
     for (uint32_t i = 0; i < s->n_quads; i++) if (s->quads[i].mat >= s->n_materials) { grt_set_error("quad material out of range"); return GRT_E_INVALID; }
     for (uint32_t i = 0; i < s->n_tris; i++) if (s->tris[i].mat >= s->n_materials) { grt_set_error("triangle material out of range"); return GRT_E_INVALID; }
     for (uint32_t i = 0; i < s->n_materials; i++) {
@@ -446,7 +449,7 @@ extern "C" int grt_scene_upload(const GrtScene* s, int device, GrtSceneHandle* o
     for (uint32_t i = 0; i < s->n_items;) {
         uint32_t ref = s->items[i] & ~GRT_LIST_LAST;
         uint32_t t = GRT_REF_TYPE(ref);
-        bool prim = t == GRT_REF_SPHERE || t == GRT_REF_QUAD || t == GRT_REF_TRI;
+        bool prim = t == GRT_REF_SPHERE || t == GRT_REF_QUAD || t == GRT_REF_TRI || t == GRT_REF_BOX;
         uint32_t n = 1;
         item2entry[i] = (uint32_t)(entries.size() / 2);
         bool last = (s->items[i] & GRT_LIST_LAST) != 0;
@@ -472,6 +475,7 @@ extern "C" int grt_scene_upload(const GrtScene* s, int device, GrtSceneHandle* o
     std::vector<GrtMedium> media(s->media, s->media + s->n_media);
     for (auto& m : media) m.boundary = remap(m.boundary);
     const uint32_t n_entries = (uint32_t)(entries.size() / 2);
+    ds.off_boxes = place(s->n_boxes * (uint32_t)sizeof(GrtBox));
     ds.off_items = place(n_entries * 8u);
     ds.off_media = place(s->n_media * (uint32_t)sizeof(GrtMedium));
     ds.off_materials = place(s->n_materials * (uint32_t)sizeof(GrtMaterial));
@@ -509,6 +513,7 @@ extern "C" int grt_scene_upload(const GrtScene* s, int device, GrtSceneHandle* o
         put(ds.off_quads, hot.data(), hot.size() * sizeof(DQuadHot));
         put(ds.off_quads_cold, cold.data(), cold.size() * sizeof(DQuadCold));
     }
+    put(ds.off_boxes, s->boxes, s->n_boxes * sizeof(GrtBox));
     put(ds.off_items, entries.data(), n_entries * 8u);
     put(ds.off_media, media.data(), s->n_media * sizeof(GrtMedium));
     put(ds.off_materials, s->materials, s->n_materials * sizeof(GrtMaterial));
@@ -516,7 +521,7 @@ extern "C" int grt_scene_upload(const GrtScene* s, int device, GrtSceneHandle* o
     put(ds.off_lights, s->lights, s->n_lights * sizeof(GrtLight));
     put(ds.off_images, s->images, s->n_images * sizeof(GrtImage));
     ds.blob_bytes = off;
-    ds.n_nodes = s->n_nodes; ds.n_spheres = s->n_spheres; ds.n_quads = s->n_quads; ds.n_items = n_entries; ds.n_media = s->n_media;
+    ds.n_nodes = s->n_nodes; ds.n_spheres = s->n_spheres; ds.n_quads = s->n_quads; ds.n_boxes = s->n_boxes; ds.n_items = n_entries; ds.n_media = s->n_media;
     ds.n_materials = s->n_materials; ds.n_textures = s->n_textures; ds.n_lights = s->n_lights; ds.n_images = s->n_images;
     ds.n_tris = s->n_tris; ds.n_perlins = s->n_perlins;
     ds.root = remap(s->root); ds.lights_mode = s->lights_mode; ds.stack_need = s->max_depth_hint;
@@ -564,7 +569,7 @@ unsigned int* grt_internal_counter(GrtSceneHandle h) { return h->d_counter; }
 
 // ---- feature-variant dispatch ------------------------------------------------
 // Each variant is a feature SUPERSET compiled as its own kernel.
-#define V_CORNELL (F_QUAD | F_LIST | F_ROTQUAD | F_QUAD_LIGHT)
+#define V_CORNELL (F_QUAD | F_BOX | F_LIST | F_ROTQUAD | F_QUAD_LIGHT)
 #define V_SMOKE (V_CORNELL | F_MEDIUM | F_ISOTROPIC)
 #define V_SPHERES (F_NODE | F_SPHERE | F_LIST | F_SPECULAR | F_TEXTURE | F_SPHERE_LIGHT | F_DEFOCUS)
 #define V_MESH (F_NODE | F_SPHERE | F_TRI | F_LIST | F_SPECULAR | F_SPHERE_LIGHT | F_TRI_LIGHT | F_TRISHADE | F_DEFOCUS)

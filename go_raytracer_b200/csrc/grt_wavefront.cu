@@ -217,7 +217,7 @@ __global__ void wf_init_slots(uint4* S3, uint32_t P) {
         if (e_ != cudaSuccess) { grt_set_error(std::string("wavefront: ") + #call + ": " + cudaGetErrorString(e_)); rc = GRT_E_CUDA; goto done; } \
     } while (0)
 
-#define V_CORNELL (F_QUAD | F_LIST | F_ROTQUAD | F_QUAD_LIGHT)
+#define V_CORNELL (F_QUAD | F_BOX | F_LIST | F_ROTQUAD | F_QUAD_LIGHT)
 #define V_SMOKE (V_CORNELL | F_MEDIUM | F_ISOTROPIC)
 
 template <uint32_t FEAT>

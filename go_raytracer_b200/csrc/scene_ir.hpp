@@ -82,6 +82,7 @@ struct TriP {                                            // objects.go:242-313
 };
 struct XformP { V3 offset; double degrees = 0; };        // transformation.go:13-19,36-42
 struct MediumP { double density; int phase; };           // medium.go:13-25
+struct BoxP { V3 mn, mx; int quads[6]; };                // NewBox, objects.go:208-240 (remembered so the six quads can share one slab test)
 
 struct Hittable {
     uint8_t type;
@@ -102,6 +103,8 @@ struct Scene {
     std::vector<XformP> xforms;
     std::vector<MediumP> media;
     std::vector<std::vector<int>> lists;
+    std::vector<BoxP> boxes;
+    std::vector<int> box_of_list;   // list payload index -> boxes index, or -1
     int world = -1;
     int lights = -1;
 
@@ -196,10 +199,11 @@ struct Scene {
     int NewTexturedTriangle(const V3 v[3], const double uv[3][2], int mat) { return NewTriangleFull(v, nullptr, uv, mat); }
     int NewTexturedTriangleWithNormals(const V3 v[3], const V3 n[3], const double uv[3][2], int mat) { return NewTriangleFull(v, n, uv, mat); }
 
-    int NewHittableList() { lists.emplace_back(); return addH(H_LIST, -1, (int)lists.size() - 1, -1); }
+    int NewHittableList() { lists.emplace_back(); box_of_list.push_back(-1); return addH(H_LIST, -1, (int)lists.size() - 1, -1); }
     void Add(int list, int obj) {
         checkH(list); checkH(obj);
         if (hittables[list].type != H_LIST) throw std::invalid_argument("Add: not a list");
+        if (box_of_list[hittables[list].a] >= 0) box_of_list[hittables[list].a] = -1;   // a box's side list was modified: no longer a plain box
         lists[hittables[list].a].push_back(obj);
     }
     // BuildBVH(list): recorded lazily; consumers run bvhHelper (bvh.go:35-61)
@@ -223,6 +227,10 @@ struct Scene {
         Add(sides, NewQuad(V3(mn.x, mn.y, mn.z), dz, dy, mat));        // left
         Add(sides, NewQuad(V3(mn.x, mx.y, mx.z), dx, neg(dz), mat));   // top
         Add(sides, NewQuad(V3(mn.x, mn.y, mn.z), dx, dz, mat));        // bottom
+        BoxP bp; bp.mn = mn; bp.mx = mx;
+        for (int i = 0; i < 6; i++) bp.quads[i] = lists[hittables[sides].a][i];
+        boxes.push_back(bp);
+        box_of_list[hittables[sides].a] = (int)boxes.size() - 1;
         return BuildBVH(sides);
     }
     int Translate(int obj, V3 offset) {

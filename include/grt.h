@@ -56,6 +56,7 @@ extern "C" {
 #define GRT_REF_TRI     3u   /* Triangle             objects.go:242  */
 #define GRT_REF_LIST    4u   /* HittableList: index of first item in items[] */
 #define GRT_REF_MEDIUM  5u   /* constantMedium       medium.go:13    */
+#define GRT_REF_BOX     6u   /* NewBox: six quads tested as one slab test  objects.go:208-240 */
 #define GRT_REF_NONE    7u   /* e.g. an empty HittableList: never hits */
 #define GRT_MAKE_REF(type, idx) (((uint32_t)(type) << GRT_REF_SHIFT) | ((uint32_t)(idx) & GRT_REF_MASK))
 #define GRT_LIST_LAST   0x80000000u  /* bit 31 of an items[] word: last item of its list */
@@ -96,6 +97,17 @@ typedef struct GrtQuad {             /* 96 B */
     float    B[3];  uint32_t id;     /* beta  = B.(p-Q), B = w x u  (== w.(u x p), objects.go:188) */
     double   n64[3]; double D64;     /* fp64 plane, used when not axis-aligned */
 } GrtQuad;
+
+/* NewBox (objects.go:208-240) builds six quads and a BVH over them.  The six quads are still emitted
+ * (quads[first_quad .. first_quad+5] in the reference's order front, right, back, left, top, bottom) and a hit
+ * reports the quad that was hit; GrtBox only lets the traversal find that quad with one slab test in the
+ * box's own frame instead of six plane tests.  world = R(obj) + T, R(v) = (rc v.x + rs v.z, v.y, -rs v.x + rc v.z). */
+typedef struct GrtBox {              /* 64 B */
+    float    mn[3]; uint32_t first_quad;
+    float    mx[3]; uint32_t flags;
+    float    T[3];  float rc;
+    float    rs;    float pad[3];
+} GrtBox;
 
 #define GRT_TRI_HAS_NORMALS 1u
 #define GRT_TRI_HAS_UV      2u
@@ -188,6 +200,7 @@ typedef struct GrtScene {
     const GrtNode*     nodes;      uint32_t n_nodes;
     const GrtSphere*   spheres;    uint32_t n_spheres;
     const GrtQuad*     quads;      uint32_t n_quads;
+    const GrtBox*      boxes;      uint32_t n_boxes;
     const GrtTri*      tris;       uint32_t n_tris;
     const GrtTriShade* tri_shade;  /* n_tris entries, or NULL if no tri has normals/uv */
     const double*      tri_v64;    /* n_tris x 9 doubles (v0,v1,v2), or NULL: fp64 vertices used to refine the

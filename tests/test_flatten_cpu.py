@@ -25,6 +25,7 @@ class FlatInterp:
         self.spheres = as_np(flat.spheres, flat.n_spheres, N.SPHERE_DTYPE)
         self.quads = as_np(flat.quads, flat.n_quads, N.QUAD_DTYPE)
         self.tris = as_np(flat.tris, flat.n_tris, N.TRI_DTYPE)
+        self.boxes = as_np(flat.boxes, flat.n_boxes, N.BOX_DTYPE)
         self.items = as_np(flat.items, flat.n_items, np.dtype("<u4"))
         self.root = flat.root
 
@@ -54,6 +55,10 @@ class FlatInterp:
                     lo, hi = max(lo, t0), min(hi, t1)
                 if ok and hi > lo:
                     stack.append(int(n["right"])); stack.append(int(n["left"]))
+            elif t == N.REF_BOX:      # the six quads of a NewBox, in order
+                fq = int(self.boxes[i]["first_quad"])
+                for f in range(5, -1, -1):
+                    stack.append((N.REF_QUAD << 28) | (fq + f))
             elif t == N.REF_QUAD:
                 q = self.quads[i]
                 den = q["n64"] @ d
@@ -131,12 +136,15 @@ def test_collapse_options_do_not_change_topology_semantics():
     """Cornell: the whole world BVH (18 leaves) is emitted as one ordered run; boxes' span-1 duplicates appear once."""
     s, _ = g.builtin_scene(6)
     flat = s.flatten()
-    assert flat.n_nodes == 0 and flat.n_quads == 18
+    assert flat.n_nodes == 0 and flat.n_quads == 18 and flat.n_boxes == 2
     items = as_np(flat.items, flat.n_items, np.dtype("<u4"))
     assert (flat.root >> 28) & 7 == N.REF_LIST
     run = items[flat.root & N.REF_MASK:]
-    assert len(run) == 18 and run[-1] & N.LIST_LAST
-    assert sorted(int(x) & N.REF_MASK for x in run) == list(range(18))
+    assert len(run) == 8 and run[-1] & N.LIST_LAST            # 5 walls + light + 2 boxes
+    kinds = sorted((int(x) >> 28) & 7 for x in run)
+    assert kinds == [N.REF_QUAD] * 6 + [N.REF_BOX] * 2
+    noprim = s.flatten(32, 4)                                    # explicit options keep box primitives too
+    assert noprim.n_boxes == 2
     # a larger tree keeps its nodes, in depth-first left-first order (left child = next node when it is a node)
     s1, _ = g.builtin_scene(1)
     f1 = s1.flatten()
