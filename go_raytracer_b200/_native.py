@@ -58,7 +58,7 @@ class GrtOptions(C.Structure):
 class GrtStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("paths", "segments", "box_tests", "sphere_tests", "quad_tests", "tri_tests",
                                           "medium_tests", "shade_diffuse", "shade_specular", "light_pdf_evals",
-                                          "nan_samples")]
+                                          "nan_samples", "warp_iterations", "lane_iterations")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}

@@ -210,26 +210,26 @@ __device__ __forceinline__ double light_pdf(const GrtLight* L, d3 o, d3 d) {
     return 0;
 }
 
-// fp32 fast path of the quad light pdf.  Returns 1 with *pdf set when the fp32 result is
-// certain (the hit is at least 1e-4 inside / outside every decision boundary: alpha, beta in
-// [0,1], t >= 0.001, |denom| >= 1e-8), 0 when the decision is within fp32 error of a boundary
-// and the fp64 evaluation must be used.
-__device__ __forceinline__ int quad_light_pdf_fast(const GrtLight* L, f3 o, f3 d, float* pdf) {
-    const float* f = L->f;
-    const f3 n = ld3(f + 9);
-    const float denom = dot(n, d);
-    const float t = __fdividef(f[15] - dot(n, o), denom);
-    const f3 planar = (o + d * t) - ld3(f);
-    const f3 w = ld3(f + 12);
-    const float alpha = dot(w, cross(planar, ld3(f + 6)));
-    const float beta = dot(w, cross(ld3(f + 3), planar));
-    const float dd = dot(d, d);
+// fp32 fast path of the quad light pdf (objects.go:152-160 + quad.Hit) on the packed DLight record.
+// Returns 1 with *pdf set when the fp32 result is certain (the hit is at least 1e-4 inside / outside
+// every decision boundary: alpha, beta in [0,1], t >= 0.001, not grazing), 0 when a decision is within
+// fp32 error of a boundary and the fp64 evaluation must be used.
+__device__ __forceinline__ int quad_light_pdf_fast(const DLight* L, f3 o, f3 d, float* pdf) {
+    const float4 P = L->plane, A = L->A, B = L->B;
+    const float denom = P.x * d.x + P.y * d.y + P.z * d.z;
+    const float t = fast_div(P.w - (P.x * o.x + P.y * o.y + P.z * o.z), denom);
+    const float px = fmaf(t, d.x, o.x), py = fmaf(t, d.y, o.y), pz = fmaf(t, d.z, o.z);
+    const float alpha = fmaf(A.x, px, fmaf(A.y, py, fmaf(A.z, pz, A.w)));
+    const float beta = fmaf(B.x, px, fmaf(B.y, py, fmaf(B.z, pz, B.w)));
+    const float dd = d.x * d.x + d.y * d.y + d.z * d.z;
+    const float rlen = rsqrtf(dd);
     const float EPS = 1e-4f;
-    const bool grazing = fabsf(denom) < 1e-3f * sqrtf(dd);
-    const bool inside = (alpha > EPS) & (alpha < 1.0f - EPS) & (beta > EPS) & (beta < 1.0f - EPS) & (t > 0.002f);
-    const bool outside = (alpha < -EPS) | (alpha > 1.0f + EPS) | (beta < -EPS) | (beta > 1.0f + EPS) | (t < 0.0005f);
-    if (grazing || !(inside || outside)) return 0;   // NaNs land here too
-    *pdf = inside ? (t * t * dd) / (fabsf(denom) * rsqrtf(dd) * f[16]) : 0.0f;
+    const float cosine = fabsf(denom) * rlen;                       // |d.n| / |d|   (objects.go:158)
+    const float lo = fminf(fminf(alpha, beta), fminf(1.0f - alpha, 1.0f - beta));   // signed distance to the nearest edge
+    const bool inside = (lo > EPS) & (t > 0.002f);
+    const bool outside = (lo < -EPS) | (t < 0.0005f);
+    if (!(cosine >= 1e-3f) || !(inside || outside)) return 0;      // grazing, near an edge / tmin, or NaN
+    *pdf = inside ? fast_div(t * t * dd, cosine * L->Qa.w) : 0.0f;  // distSquared / (cosine * area)
     return 1;
 }
 
@@ -355,7 +355,11 @@ __device__ __forceinline__ ShadeResult shade_vertex(const SceneView& sv, const R
             r1 = rng.next(); r2 = rng.next();
             from_light = true;
             const GrtLight* L = lights + li;
-            if ((FEAT & F_QUAD_LIGHT) && L->type == GRT_LIGHT_QUAD) dir = (ld3(L->f) + ld3(L->f + 3) * r1 + ld3(L->f + 6) * r2) - s.p;   // objects.go:161-165
+            if ((FEAT & F_QUAD_LIGHT) && L->type == GRT_LIGHT_QUAD) {   // objects.go:161-165
+                const DLight* D = sv.dlights() + li;
+                const float4 Q = D->Qa, U = D->U, V = D->V;
+                dir = mk3(fmaf(V.x, r2, fmaf(U.x, r1, Q.x)) - s.p.x, fmaf(V.y, r2, fmaf(U.y, r1, Q.y)) - s.p.y, fmaf(V.z, r2, fmaf(U.z, r1, Q.z)) - s.p.z);
+            }
             else dir = tof3(light_random<FEAT>(L, tod3(s.p), r1, r2));
         }
     } else {
@@ -375,7 +379,7 @@ __device__ __forceinline__ ShadeResult shade_vertex(const SceneView& sv, const R
         for (uint32_t i = 0; i < nl; i++) {
             const GrtLight* L = lights + i;
             float pv;
-            if (!((FEAT & F_QUAD_LIGHT) && L->type == GRT_LIGHT_QUAD && quad_light_pdf_fast(L, s.p, dir, &pv))) {
+            if (!((FEAT & F_QUAD_LIGHT) && L->type == GRT_LIGHT_QUAD && quad_light_pdf_fast(sv.dlights() + i, s.p, dir, &pv))) {
                 // within fp32 error of a decision boundary (or not a quad): the reference's fp64 arithmetic.
                 // A direction sampled ON this light is regenerated in fp64 so that it cannot fall off its edge.
                 d3 p64 = tod3(s.p);
@@ -422,22 +426,31 @@ __device__ __forceinline__ void apply_factor(f3& T, uint32_t& zinfo, f3 w, int s
     }
     T = T * w;
 }
-__device__ __forceinline__ f3 recip_factor(f3 T) { return mk3(fminf(__frcp_rn(T.x), 1e30f), fminf(__frcp_rn(T.y), 1e30f), fminf(__frcp_rn(T.z), 1e30f)); }
+__device__ __forceinline__ float4 recip_factor(f3 T) { return make_float4(fast_div(1.0f, T.x), fast_div(1.0f, T.y), fast_div(1.0f, T.z), 0.0f); }
 
 // L0 = P0 * min(1, M / max_j sum(P_j)),  P0 = T (x) E,  sum(P_j) = P0 . rstack[j] over the components whose
 // suffix from j holds no zero factor.  `stride` lets the wavefront variant keep the stack depth-major in HBM.
 template <class StackPtr>
 __device__ __forceinline__ f3 unwind_clamp(f3 T, uint32_t zinfo, f3 E, StackPtr rstack, int sp, float max_contribution, size_t stride = 1) {
     f3 L = T * E;
-    float worst = 0.0f;
-    const int zx = (int)(zinfo & 255u), zy = (int)((zinfo >> 8) & 255u), zz = (int)((zinfo >> 16) & 255u);
-    for (int i = 0; i < sp; i++) {
-        const auto rj = rstack[(size_t)i * stride];
-        float sj = (i >= zx ? L.x * rj.x : 0.0f) + (i >= zy ? L.y * rj.y : 0.0f) + (i >= zz ? L.z * rj.z : 0.0f);
-        worst = fmaxf(worst, sj);
+    float worst = 0.0f;   // fmaxf drops the NaN of 0 * inf (an underflowed T component), which contributes nothing anyway
+    if (zinfo == 0u) {
+        for (int i = 0; i < sp; i++) {
+            const float4 rj = rstack[(size_t)i * stride];
+            worst = fmaxf(worst, fmaf(L.x, rj.x, fmaf(L.y, rj.y, L.z * rj.z)));
+        }
+    } else {
+        const int zx = (int)(zinfo & 255u), zy = (int)((zinfo >> 8) & 255u), zz = (int)((zinfo >> 16) & 255u);
+        for (int i = 0; i < sp; i++) {
+            const float4 rj = rstack[(size_t)i * stride];
+            float sj = (i >= zx ? L.x * rj.x : 0.0f) + (i >= zy ? L.y * rj.y : 0.0f) + (i >= zz ? L.z * rj.z : 0.0f);
+            worst = fmaxf(worst, sj);
+        }
+        if (zinfo & (1u << 24)) L.x = 0.0f;
+        if (zinfo & (1u << 25)) L.y = 0.0f;
+        if (zinfo & (1u << 26)) L.z = 0.0f;
     }
-    if (worst > max_contribution) L = L * __fdividef(max_contribution, worst);
-    if (zinfo >> 24) { if (zinfo & (1u << 24)) L.x = 0.0f; if (zinfo & (1u << 25)) L.y = 0.0f; if (zinfo & (1u << 26)) L.z = 0.0f; }
+    if (worst > max_contribution) L = L * fast_div(max_contribution, worst);
     return L;
 }
 

@@ -42,12 +42,17 @@ struct DQuadCold {
     double n64[3]; double D64;
 };
 
+// Device-internal fp32 record of a quad light (fast path of dev_shade.cuh), built at upload from GrtLight.p:
+// the re-intersection of objects.go:152-160 needs the plane and the two affine interior forms, sampling
+// (objects.go:161-165) needs Q, u, v.
+struct DLight { float4 plane, A, B, Qa, U, V; };   // Qa.w = area
+
 // The small, hot arrays live in one blob (byte offsets below) so a block can
 // stage the whole thing in shared memory when it fits; large arrays stay in HBM.
 struct DevScene {
     const unsigned char* blob;   // HBM copy of the blob
     uint32_t blob_bytes;
-    uint32_t off_nodes, off_spheres, off_quads, off_quads_cold, off_boxes, off_items, off_media, off_materials, off_textures, off_lights, off_images;
+    uint32_t off_nodes, off_spheres, off_quads, off_quads_cold, off_boxes, off_items, off_media, off_materials, off_textures, off_lights, off_dlights, off_images;
     uint32_t n_nodes, n_spheres, n_quads, n_boxes, n_items, n_media, n_materials, n_textures, n_lights, n_images;
     const GrtTri* tris;          // HBM
     const GrtTriShade* tri_shade;
@@ -73,6 +78,7 @@ struct SceneView {
     __device__ __forceinline__ const GrtMaterial* materials() const { return (const GrtMaterial*)(base + ds->off_materials); }
     __device__ __forceinline__ const GrtTexture* textures() const { return (const GrtTexture*)(base + ds->off_textures); }
     __device__ __forceinline__ const GrtLight* lights() const { return (const GrtLight*)(base + ds->off_lights); }
+    __device__ __forceinline__ const DLight* dlights() const { return (const DLight*)(base + ds->off_dlights); }
     __device__ __forceinline__ const GrtImage* images() const { return (const GrtImage*)(base + ds->off_images); }
 };
 
@@ -244,10 +250,14 @@ __device__ __forceinline__ int box_prim_hit(const GrtBox* bx, const RayD& r, flo
     if (!(t_enter <= t_exit)) return -1;
     // faces: 0 front z=max, 1 right x=max, 2 back z=min, 3 left x=min, 4 top y=max, 5 bottom y=min
     // entering through axis a: the min face when d_a > 0, else the max face; leaving: the other way round
-    int f_enter, f_exit;
-    float d_enter, d_exit;
-    if (lox >= loy && lox >= loz) { f_enter = dx > 0 ? 3 : 1; d_enter = dx; } else if (loy >= loz) { f_enter = dy > 0 ? 5 : 4; d_enter = dy; } else { f_enter = dz > 0 ? 2 : 0; d_enter = dz; }
-    if (hix <= hiy && hix <= hiz) { f_exit = dx > 0 ? 1 : 3; d_exit = dx; } else if (hiy <= hiz) { f_exit = dy > 0 ? 4 : 5; d_exit = dy; } else { f_exit = dz > 0 ? 0 : 2; d_exit = dz; }
+    // (selects, no branches: the three axes are equally likely and would split the warp three ways)
+    const int fx_in = dx > 0 ? 3 : 1, fy_in = dy > 0 ? 5 : 4, fz_in = dz > 0 ? 2 : 0;
+    const bool ex = (lox >= loy) & (lox >= loz), ey = loy >= loz;
+    const int f_enter = ex ? fx_in : (ey ? fy_in : fz_in);
+    const float d_enter = ex ? dx : (ey ? dy : dz);
+    const bool xx = (hix <= hiy) & (hix <= hiz), xy = hiy <= hiz;
+    const int f_exit = xx ? (4 - fx_in) : (xy ? (9 - fy_in) : (2 - fz_in));   // the opposite face of the same axis
+    const float d_exit = xx ? dx : (xy ? dy : dz);
     near_tmin = (fabsf((t_enter - tmin) * d_enter) < 2.5e-4f) | (fabsf((t_exit - tmin) * d_exit) < 2.5e-4f);
     if (tmin <= t_enter && t_enter <= tmax && f_enter != excl_face) { t_out = t_enter; return f_enter; }
     if (tmin <= t_exit && t_exit <= tmax && f_exit != excl_face) { t_out = t_exit; return f_exit; }

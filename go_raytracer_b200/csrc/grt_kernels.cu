@@ -162,9 +162,9 @@ __global__ void __launch_bounds__(GRT_MEGA_THREADS, GRT_MEGA_MIN_BLOCKS) render_
     f3 T = mk3(1, 1, 1);
     uint32_t zinfo = 0;
     int sp = 0;
-    f3 rstack[WEIGHT_STACK];
+    float4 rstack[WEIGHT_STACK];
     // stats
-    uint32_t st_paths = 0, st_segments = 0, st_diffuse = 0, st_specular = 0, st_lightpdf = 0, st_nan = 0;
+    uint32_t st_paths = 0, st_segments = 0, st_diffuse = 0, st_specular = 0, st_lightpdf = 0, st_nan = 0, st_iters = 0;
     TraceCounters tc;
     tc.box = tc.sphere = tc.quad = tc.tri = tc.medium = 0;
 
@@ -222,6 +222,7 @@ __global__ void __launch_bounds__(GRT_MEGA_THREADS, GRT_MEGA_MIN_BLOCKS) render_
             if (pix_cur == 0xffffffffu) break;
             continue;
         }
+        if (STATS && lane == 0) st_iters++;
         if (!active) continue;
 
         // ---- one path segment: trace ------------------------------------------
@@ -255,7 +256,7 @@ __global__ void __launch_bounds__(GRT_MEGA_THREADS, GRT_MEGA_MIN_BLOCKS) render_
                     if (R.value.x == 0.0f && R.value.y == 0.0f && R.value.z == 0.0f) { terminate = true; }  // weight 0: the sample is 0 whatever follows
                     else {
                         // 1/T_before_j; a zero component stays zero in P0 as well, so its reciprocal is irrelevant
-                        rstack[sp++] = mk3(fminf(__frcp_rn(T.x), 1e30f), fminf(__frcp_rn(T.y), 1e30f), fminf(__frcp_rn(T.z), 1e30f));
+                        rstack[sp++] = recip_factor(T);
                         apply_factor(T, zinfo, R.value, sp);
                     }
                 }
@@ -283,10 +284,10 @@ __global__ void __launch_bounds__(GRT_MEGA_THREADS, GRT_MEGA_MIN_BLOCKS) render_
     }
 
     if (STATS) {
-        unsigned long long v[11] = {st_paths, st_segments, tc.box, tc.sphere, tc.quad, tc.tri, tc.medium, st_diffuse, st_specular, st_lightpdf, st_nan};
+        unsigned long long v[13] = {st_paths, st_segments, tc.box, tc.sphere, tc.quad, tc.tri, tc.medium, st_diffuse, st_specular, st_lightpdf, st_nan, st_iters, st_segments};
         unsigned long long* dst = (unsigned long long*)P.stats;
 #pragma unroll
-        for (int i = 0; i < 11; i++) {
+        for (int i = 0; i < 13; i++) {
             unsigned long long x = v[i];
             for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(FULL, x, off);
             if (lane == 0 && x) atomicAdd(dst + i, x);
@@ -481,6 +482,7 @@ extern "C" int grt_scene_upload(const GrtScene* s, int device, GrtSceneHandle* o
     ds.off_materials = place(s->n_materials * (uint32_t)sizeof(GrtMaterial));
     ds.off_textures = place(s->n_textures * (uint32_t)sizeof(GrtTexture));
     ds.off_lights = place(s->n_lights * (uint32_t)sizeof(GrtLight));
+    ds.off_dlights = place(s->n_lights * (uint32_t)sizeof(DLight));
     ds.off_images = place(s->n_images * (uint32_t)sizeof(GrtImage));
     if (off == 0) off = 16;
     std::vector<unsigned char> blob(off, 0);
@@ -519,6 +521,24 @@ extern "C" int grt_scene_upload(const GrtScene* s, int device, GrtSceneHandle* o
     put(ds.off_materials, s->materials, s->n_materials * sizeof(GrtMaterial));
     put(ds.off_textures, s->textures, s->n_textures * sizeof(GrtTexture));
     put(ds.off_lights, s->lights, s->n_lights * sizeof(GrtLight));
+    {
+        std::vector<DLight> dl(s->n_lights);
+        for (uint32_t i = 0; i < s->n_lights; i++) {
+            memset(&dl[i], 0, sizeof(DLight));
+            if (s->lights[i].type != GRT_LIGHT_QUAD) continue;
+            const double* p = s->lights[i].p;   // Q[3], u[3], v[3], n[3], w[3], D, area
+            const double *Q = p, *u = p + 3, *v = p + 6, *n = p + 9, *w = p + 12;
+            double A[3] = {v[1] * w[2] - v[2] * w[1], v[2] * w[0] - v[0] * w[2], v[0] * w[1] - v[1] * w[0]};   // v x w: alpha = A.(p - Q)
+            double B[3] = {w[1] * u[2] - w[2] * u[1], w[2] * u[0] - w[0] * u[2], w[0] * u[1] - w[1] * u[0]};   // w x u: beta  = B.(p - Q)
+            dl[i].plane = make_float4((float)n[0], (float)n[1], (float)n[2], (float)p[15]);
+            dl[i].A = make_float4((float)A[0], (float)A[1], (float)A[2], (float)-(A[0] * Q[0] + A[1] * Q[1] + A[2] * Q[2]));
+            dl[i].B = make_float4((float)B[0], (float)B[1], (float)B[2], (float)-(B[0] * Q[0] + B[1] * Q[1] + B[2] * Q[2]));
+            dl[i].Qa = make_float4((float)Q[0], (float)Q[1], (float)Q[2], (float)p[16]);
+            dl[i].U = make_float4((float)u[0], (float)u[1], (float)u[2], 0.0f);
+            dl[i].V = make_float4((float)v[0], (float)v[1], (float)v[2], 0.0f);
+        }
+        put(ds.off_dlights, dl.data(), dl.size() * sizeof(DLight));
+    }
     put(ds.off_images, s->images, s->n_images * sizeof(GrtImage));
     ds.blob_bytes = off;
     ds.n_nodes = s->n_nodes; ds.n_spheres = s->n_spheres; ds.n_quads = s->n_quads; ds.n_boxes = s->n_boxes; ds.n_items = n_entries; ds.n_media = s->n_media;

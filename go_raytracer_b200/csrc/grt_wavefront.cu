@@ -193,8 +193,7 @@ __global__ void __launch_bounds__(256) wf_shade(const __grid_constant__ WfParams
     if (R.kind == SHADE_SPECULAR) apply_factor(T, zinfo, R.value, sp);
     else {
         if (R.value.x == 0.0f && R.value.y == 0.0f && R.value.z == 0.0f) { wf_finish_path(P, slot, s3.x, mk3(0, 0, 0)); return; }
-        f3 r = recip_factor(T);
-        P.rstack[(size_t)sp * P.P + slot] = make_float4(r.x, r.y, r.z, 0.0f);
+        P.rstack[(size_t)sp * P.P + slot] = recip_factor(T);
         sp++;
         apply_factor(T, zinfo, R.value, sp);
     }

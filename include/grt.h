@@ -256,6 +256,8 @@ typedef struct GrtStats {            /* event counters for the roofline table */
     uint64_t box_tests, sphere_tests, quad_tests, tri_tests, medium_tests;
     uint64_t shade_diffuse, shade_specular, light_pdf_evals;
     uint64_t nan_samples;
+    uint64_t warp_iterations;        /* megakernel: loop iterations summed over warps          */
+    uint64_t lane_iterations;        /* ... and the number of lanes that traced a segment in them */
 } GrtStats;
 
 /* ---- ray batch (parity checks 1 and 2) ----------------------------------- */

@@ -32,7 +32,7 @@ def test_struct_sizes_match_header():
     # sizes the device code relies on (include/grt.h)
     assert C.sizeof(N.GrtCamera) == 16 + 6 * 24 + 8 + 24 + 8
     assert C.sizeof(N.GrtOptions) == 48
-    assert C.sizeof(N.GrtStats) == 88
+    assert C.sizeof(N.GrtStats) == 104
     assert g.lib().grt_abi_version() == 1
 
 
