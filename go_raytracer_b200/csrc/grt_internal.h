@@ -6,10 +6,10 @@
 
 #define GRT_MEGA_THREADS 128
 #ifndef GRT_MEGA_MIN_BLOCKS
-#define GRT_MEGA_MIN_BLOCKS 5   /* 96 registers, 20 warps/SM: measured best of 4/5/6 (profiles/) */
+#define GRT_MEGA_MIN_BLOCKS 6   /* 80 registers, 24 warps/SM: measured best of 4/5/6 (profiles/README.md) */
 #endif
 // the scene blob is staged into shared memory when every resident block can hold a copy
-#define GRT_STAGE_MAX_BYTES (40u * 1024u)
+#define GRT_STAGE_MAX_BYTES (36u * 1024u)
 
 namespace grtd { struct DevScene; struct DevCamera; }
 
