@@ -205,3 +205,72 @@ def test_wavefront_variant_matches_megakernel(sid, w, spp):
     ref, _, _ = dev.render(cam, variant=g.GRT_VARIANT_MEGAKERNEL, sample_first=1, sample_stride=2, window=(2, 2, 20, 18))
     f2 = np.isfinite(part) & np.isfinite(ref)
     assert np.allclose(part[f2], ref[f2], rtol=1e-4, atol=1e-4)
+
+
+def _box_scene():
+    """Boxes in every configuration the box primitive must handle: plain, rotated + translated, nested in a BVH with
+    other primitives, a flat (degenerate) one, and one carrying an image texture (needs the quad's alpha/beta)."""
+    sc = g.Scene()
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 255, size=(16, 32, 3), dtype=np.uint8)
+    tex = sc.NewImageTextureFromArray(img)
+    white = sc.NewLambertian((.7, .7, .7))
+    tm = sc.NewTexturedLambertian(tex)
+    objs = [sc.NewBox((0, 0, 0), (1, 2, 3), white),
+            sc.Translate(sc.RotateY(sc.NewBox((0, 0, 0), (2, 1, 1), tm), 33.0), (4, 0.5, -1)),
+            sc.Translate(sc.NewBox((-1, -1, -1), (1, 1, 1), tm), (-4, 0, 2)),
+            sc.NewBox((6, 0, 0), (8, 0, 2), white),                     # zero height: stays six quads
+            sc.NewSphere((2, 4, 1), 0.8, white)]
+    for k in range(12):
+        c = rng.uniform(-6, 8, size=3)
+        objs.append(sc.Translate(sc.RotateY(sc.NewBox((0, 0, 0), tuple(rng.uniform(0.3, 1.5, size=3)), white), float(rng.uniform(-90, 90))), tuple(c)))
+    light = sc.NewQuad((-2, 9, -2), (4, 0, 0), (0, 0, 4), sc.NewDiffuseLight((5, 5, 5)))
+    objs.append(light)
+    sc.set_world(sc.BuildBVH(sc.NewHittableList(objs)))
+    sc.set_lights(sc.NewHittableList([light]))
+    return sc
+
+
+def test_box_primitive_matches_six_quads():
+    sc = _box_scene()
+    ow = O.OracleWorld(sc)
+    rng = np.random.default_rng(11)
+    n = 60000
+    o = rng.uniform(-9, 11, size=(n, 3))
+    o[: n // 4] = rng.uniform(0.05, 0.95, size=(n // 4, 3)) * (1, 2, 3)       # a quarter of the rays start INSIDE the first box
+    d = rng.normal(size=(n, 3)) * rng.uniform(0.2, 40, size=(n, 1))
+    rays = PU.make_rays(o, d)
+    oh = ow.trace_batch(rays, audit_eps=1e-5)
+    for collapse in (None, (0, 0)):                                        # box primitives on / reference tree
+        dev = g.DeviceScene(sc) if collapse is None else g.DeviceScene(sc, 0, *collapse)
+        flat = sc.flatten() if collapse is None else sc.flatten(*collapse)
+        assert (flat.n_boxes > 10) == (collapse is None)
+        gh = dev.trace_batch(rays)
+        r = PU.compare_hits(gh, oh, t_rel=T_REL)
+        assert r["id_mismatch_unflagged"] == 0 and r["t_bad"] == 0, r
+        ok = (oh["id"] >= 0) & (oh["flags"] == 0)
+        # alpha/beta of the hit quad (needed by the image texture) survive the box shortcut
+        quad_like = ok & (np.abs(oh["u"]) <= 1) & (np.abs(oh["v"]) <= 1)
+        assert np.abs(gh["u"][quad_like] - oh["u"][quad_like]).max() < 5e-4
+        assert np.abs(gh["v"][quad_like] - oh["v"][quad_like]).max() < 5e-4
+    # interval variants used by constantMedium.Hit (medium.go:29-35): whole line, then past the first hit
+    line = PU.make_rays(o[: n // 4], d[: n // 4], tmin=-np.inf)
+    _ = PU.compare_hits(g.DeviceScene(sc).trace_batch(line), ow.trace_batch(line, audit_eps=1e-5), t_rel=T_REL)
+    assert _["id_mismatch_unflagged"] == 0 and _["t_bad"] == 0, _
+
+
+def test_flatten_options_do_not_change_the_image():
+    """Ordered leaf runs / box primitives vs the reference's tree node for node: same samples, same image."""
+    sc = _box_scene()
+    cam = g.Camera()
+    cam.AspectRatio, cam.Width, cam.SamplesPerPixel, cam.MaxDepth = 1.0, 40, 16, 20
+    cam.VerticalFOV, cam.Background = 60, (0.1, 0.1, 0.15)
+    cam.PositionCamera((2, 5, 16), (1, 1, 0), (0, 1, 0))
+    dcam = g.derive_camera(cam.config())
+    a, _, _ = g.DeviceScene(sc).render(dcam)
+    b, _, _ = g.DeviceScene(sc, 0, 0, 0).render(dcam)
+    assert np.isfinite(a).all() and a.mean() > 0
+    close = np.isclose(a, b, rtol=1e-4, atol=1e-4)
+    assert close.mean() > 0.995          # identical paths except where an fp32 tie falls the other way
+    os_, _, _, _ = O.OracleWorld(sc).render(cam.config(), use_exclusion=True)
+    assert np.isclose(a, os_, rtol=1e-3, atol=1e-3).mean() > 0.99
