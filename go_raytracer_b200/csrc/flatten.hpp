@@ -420,7 +420,13 @@ class Flattener {
                 // NewQuad (objects.go:129-141)
                 V3 n = cross(u, v);
                 double nn = dot(n, n);
-                if (!(nn > 0)) throw std::runtime_error("degenerate quad");
+                if (!(nn > 0)) {
+                    // u x v = 0: NewQuad's normal, D and w are NaN (objects.go:132-136), every comparison in
+                    // quad.Hit is false and the quad can never be hit — emit nothing, keep its extent
+                    e.ref = GRT_MAKE_REF(GRT_REF_NONE, 0);
+                    e.box.add(Q); e.box.add(Q + u); e.box.add(Q + v); e.box.add(Q + u + v);
+                    break;
+                }
                 V3 normal = n * (1 / length(n));
                 double D = dot(normal, Q);
                 V3 w = n * (1 / nn);
