@@ -35,6 +35,13 @@ COSTS = {
 }
 
 
+# Event counts per path of the REFERENCE algorithm on this workload (the oracle's counters: reference BVH, every
+# continuation traced, SURVEY.md 8d "events counted by the oracle").  Used when the CPU leg is skipped; the CPU leg
+# re-measures them.  Source: oracle, cornellBox 1024x1024 x 16 spp, seed 0xC0FFEE.
+ORACLE_EVENTS_PER_PATH = {"paths": 1.0, "box_tests": 27.06, "quad_tests": 17.55, "sphere_tests": 0.0, "tri_tests": 0.0,
+                          "medium_tests": 0.0, "shade_diffuse": 1.925, "shade_specular": 0.0, "light_pdf_evals": 1.925}
+
+
 def algorithmic_cost(stats):
     paths = max(1, stats["paths"])
     fl = sum(stats[k] * c[0] for k, c in COSTS.items())
@@ -238,8 +245,26 @@ def run_ours(args):
         sc2 = g.DeviceScene(s2, local)
         _, _, st = sc2.render(cam2, seed=args.seed, variant=N.GRT_VARIANT_MEGAKERNEL, want_stats=True)   # event counts are variant-independent
         sc2.close()
-        flops_pp, bytes_pp = algorithmic_cost(st)
-        bytes_pp += 12.0 / S2                                       # fp32 RGB write per pixel, amortised
+        executed = {k: st[k] / st["paths"] for k in COSTS}            # what THIS kernel executes (ordered runs, box slabs, zero-weight cut-off)
+        ref_events = dict(ORACLE_EVENTS_PER_PATH)
+        ref_src = "frozen (bench.py:ORACLE_EVENTS_PER_PATH)"
+        hbm_bytes_pp = 12.0 / S2                                      # what must reach HBM: one fp32 RGB store per pixel
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            # ---- CPU baseline (oracle port) on a bounded sample; it also counts the reference algorithm's events
+            from oracle import oracle_py as O
+            cores = os.cpu_count() or 1
+            sb, cfgb = g.builtin_scene(6, width=args.width, spp=args.cpu_spp)
+            ow = O.OracleWorld(sb)
+            camb = O.derived_camera(cfgb)
+            _, _, ost, sec = ow.render(cfgb, nthreads=cores, want_stats=True)
+            pb = camb.width * camb.height * camb.spp_sqrt ** 2
+            cpu = {"value": pb / sec / 1e6, "unit": "Mpaths/s", "cores": cores, "kind": "port",
+                   "sample": f"{camb.width}x{camb.height} x {camb.spp_sqrt ** 2} spp (full resolution, reduced spp), {sec:.1f} s, "
+                             "C++ fp64 restatement of the Go renderer (no Go toolchain here); faster than the Go binary would be"}
+            ref_events = {k: ost[k] / ost["paths"] for k in COSTS}
+            ref_src = "oracle counters of the cpu_baseline run"
+        flops_pp, onchip_bytes_pp = algorithmic_cost(dict({k: v for k, v in ref_events.items()}, paths=1.0))
         kernel_ms = ms / args.steps                                  # the megakernel is >99.9 % of the step
         props = torch.cuda.get_device_properties(local)
         peaks = {}
@@ -252,32 +277,27 @@ def run_ours(args):
         per_gpu_paths = paths / world
         ach_tf = per_gpu_paths * flops_pp / (kernel_ms / 1e3) / 1e12
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        ach_gbs = per_gpu_paths * bytes_pp / (kernel_ms / 1e3) / 1e9
+        ach_gbs = per_gpu_paths * hbm_bytes_pp / (kernel_ms / 1e3) / 1e9
+        traffic = None
+        try:   # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel at this size
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"{args.width}x{args.spp}")
+        except Exception:
+            pass
         roofline = {"kernel": "render_mega_kernel" if variant == 0 else "wavefront kernels",
                     "bound": "fp32_issue", "achieved": ach_tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach_tf / fp32_peak,
                     "peak_source": f"SMs({props.multi_processor_count}) x 128 lanes x 2 x {sm_mhz:.0f} MHz observed during the run",
-                    "flops_per_path": flops_pp, "bytes_per_path": bytes_pp, "events_per_path": {k: st[k] / st["paths"] for k in COSTS},
-                    "traffic": None,
+                    "flops_per_path": flops_pp, "onchip_bytes_per_path": onchip_bytes_pp, "hbm_bytes_per_path": hbm_bytes_pp,
+                    "events_per_path": ref_events, "events_source": ref_src, "executed_events_per_path": executed,
+                    "lanes_per_warp_iteration": st["lane_iterations"] / max(1, st["warp_iterations"]),
+                    "traffic": traffic,
                     "hbm": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                             "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"},
-                    "note": "not tensor-core work (no dense contraction); scene is shared-memory resident, so the binding "
-                            "roofline is FP32 issue, the HBM line is reported for completeness"}
-        # ---- CPU baseline (oracle port) on a bounded sample -------------------------------------------
-        cpu = None
-        if world == 1 and not args.no_cpu:
-            from oracle import oracle_py as O
-            cores = os.cpu_count() or 1
-            sb, cfgb = g.builtin_scene(6, width=args.width, spp=args.cpu_spp)
-            ow = O.OracleWorld(sb)
-            camb = O.derived_camera(cfgb)
-            _, _, _, sec = ow.render(cfgb, nthreads=cores)
-            pb = camb.width * camb.height * camb.spp_sqrt ** 2
-            cpu = {"value": pb / sec / 1e6, "unit": "Mpaths/s", "cores": cores, "kind": "port",
-                   "sample": f"{camb.width}x{camb.height} x {camb.spp_sqrt ** 2} spp (full resolution, reduced spp), {sec:.1f} s, "
-                             "C++ fp64 restatement of the Go renderer (no Go toolchain here); faster than the Go binary would be"}
+                    "note": "not tensor-core work (no dense contraction); the 4 KB scene is shared-memory resident, so the binding "
+                            "roofline is FP32 issue (SURVEY.md 8d); the hbm object is the HBM roofline on the bytes that must reach "
+                            "HBM (one RGB store per pixel), reported to show the kernel is nowhere near it"}
         line = {"metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": "f32 (f64 for light pdfs and rotated-quad planes)", "data": "synthetic",
+                "dtype": "f32 (f64 only for the winning hit's t and for decisions within fp32 error of a boundary)", "data": "synthetic",
                 "config": dict(workload(args), variant=args.variant, parallelism=f"spp-shard x{world} + ncclReduce",
                                l2="flushed between steps (256 MiB write); per-step CUDA events summed"),
                 "clocks": clocks,

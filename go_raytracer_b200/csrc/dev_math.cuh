@@ -57,7 +57,15 @@ __host__ __device__ __forceinline__ void philox4x32_10(uint32_t& c0, uint32_t& c
 
 // uniform in (0,1): (2*(w>>9)+1) / 2^24 — an odd multiple of 2^-24, exactly
 // representable in fp32 and strictly inside the interval.
-__host__ __device__ __forceinline__ float u01(uint32_t w) { return (float)(2u * (w >> 9) + 1u) * (1.0f / 16777216.0f); }
+// Built from bits: 0x3f800000 | (w>>9) is 1 + k/2^23 in [1,2); subtracting 1 - 2^-24 gives k/2^23 + 2^-24 exactly
+// (the result is representable, so the subtraction is exact).  Two instructions, no int->float conversion.
+__host__ __device__ __forceinline__ float u01(uint32_t w) {
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(0x3f800000u | (w >> 9)) - 0.99999994f;   // 0.99999994f == 1 - 2^-24
+#else
+    return (float)(2u * (w >> 9) + 1u) * (1.0f / 16777216.0f);
+#endif
+}
 
 #define GRT_STREAM_SHADE 0u
 #define GRT_STREAM_MEDIUM 1u

@@ -333,8 +333,8 @@ __device__ bool closest_hit(const SceneView& sv, uint32_t root, const RayD& r, f
         if ((FEAT & F_QUAD) && type == GRT_REF_QUAD) {
             const DQuadHot* q = sv.quads() + idx;
             if (STATS) tc->quad += n;
-#pragma unroll 2
-            for (uint32_t k = 0; k < n; k++) {
+            // one quad: branch-free candidate test + predicated update of (tmax, ref)
+            auto one = [&](uint32_t k) {
                 float t, a, b;
                 bool unc;
                 bool ok = quad_hit(q + k, r, tmin, tmax, t, a, b, unc);
@@ -343,6 +343,19 @@ __device__ bool closest_hit(const SceneView& sv, uint32_t root, const RayD& r, f
                 if (FEAT & F_DUPIDS) ok = ok && (sv.quads_cold()[idx + k].id != excl);
                 else ok = ok & ((ref + k) != excl_ref);
                 if (ok) { tmax = t; hit.ref = ref + k; hit.u = a; hit.v = b; }
+            };
+            // short runs (every run of a small scene) are straight-line code: no loop counters, and the
+            // scheduler can overlap the loads of one quad with the arithmetic of the previous one
+            switch (n) {
+                case 1: one(0); break;
+                case 2: one(0); one(1); break;
+                case 3: one(0); one(1); one(2); break;
+                case 4: one(0); one(1); one(2); one(3); break;
+                case 5: one(0); one(1); one(2); one(3); one(4); break;
+                case 6: one(0); one(1); one(2); one(3); one(4); one(5); break;
+                default:
+#pragma unroll 2
+                    for (uint32_t k = 0; k < n; k++) one(k);
             }
             return true;
         }

@@ -122,26 +122,30 @@ __global__ void __launch_bounds__(GRT_MEGA_THREADS, GRT_MEGA_MIN_BLOCKS) render_
     bool alloc_on_nxt = false;               // samples are being handed out from pix_nxt
     bool exhausted = false;                  // no more pixels to claim
 
+    // pixel coordinates packed as (y << 16) | x.  One integer division per claimed BLOCK of pixels (next to the
+    // atomic, so it is not speculated into the loop), then incremental.
+    uint32_t blk_x = 0, blk_y = 0, claimed_xy = 0;
     auto claim_pixel = [&]() -> uint32_t {
         if (blk_next == blk_end && !exhausted) {
             uint32_t base = 0;
             if (lane == 0) base = atomicAdd(P.counter, P.claim);
             base = __shfl_sync(FULL, base, 0);
             if (base >= P.n_pixels) { exhausted = true; }
-            else { blk_next = base; blk_end = min(base + P.claim, P.n_pixels); }
+            else {
+                blk_next = base; blk_end = min(base + P.claim, P.n_pixels);
+                blk_y = base / (uint32_t)P.ww; blk_x = base - blk_y * (uint32_t)P.ww;
+            }
         }
-        if (blk_next < blk_end) return blk_next++;
+        if (blk_next < blk_end) {
+            claimed_xy = (((uint32_t)P.y0 + blk_y) << 16) | ((uint32_t)P.x0 + blk_x);
+            if (++blk_x == (uint32_t)P.ww) { blk_x = 0; blk_y++; }
+            return blk_next++;
+        }
         return 0xffffffffu;
-    };
-    // pixel coordinates packed as (y << 16) | x, one integer division per PIXEL instead of per path
-    auto pixel_xy = [&](uint32_t q) -> uint32_t {
-        if (q == 0xffffffffu) return 0u;
-        uint32_t row = q / (uint32_t)P.ww;
-        return (((uint32_t)P.y0 + row) << 16) | ((uint32_t)P.x0 + (q - row * (uint32_t)P.ww));
     };
     pix_cur = claim_pixel();
     if (pix_cur == 0xffffffffu) return;
-    uint32_t xy_cur = pixel_xy(pix_cur), xy_nxt = 0;
+    uint32_t xy_cur = claimed_xy, xy_nxt = 0;
 
     // lane state
     bool active = false;
@@ -196,7 +200,7 @@ __global__ void __launch_bounds__(GRT_MEGA_THREADS, GRT_MEGA_MIN_BLOCKS) render_
             if (!need) break;
             // this pixel is used up: move allocation to the next pixel, at most one ahead
             if (alloc_on_nxt) break;
-            if (pix_nxt == 0xffffffffu) { pix_nxt = claim_pixel(); xy_nxt = pixel_xy(pix_nxt); }
+            if (pix_nxt == 0xffffffffu) { pix_nxt = claim_pixel(); xy_nxt = claimed_xy; }
             if (pix_nxt == 0xffffffffu) break;
             alloc_on_nxt = true; k_alloc = 0;
         }
@@ -218,7 +222,7 @@ __global__ void __launch_bounds__(GRT_MEGA_THREADS, GRT_MEGA_MIN_BLOCKS) render_
             acc0 = acc1; acc1 = mk3(0, 0, 0);
             if (active) my_parity = 0u;   // survivors were on pix_nxt
             if (alloc_on_nxt) { pix_cur = pix_nxt; xy_cur = xy_nxt; pix_nxt = 0xffffffffu; alloc_on_nxt = false; }
-            else { pix_cur = claim_pixel(); xy_cur = pixel_xy(pix_cur); k_alloc = 0; }
+            else { pix_cur = claim_pixel(); xy_cur = claimed_xy; k_alloc = 0; }
             if (pix_cur == 0xffffffffu) break;
             continue;
         }
@@ -278,7 +282,7 @@ __global__ void __launch_bounds__(GRT_MEGA_THREADS, GRT_MEGA_MIN_BLOCKS) render_
                 // unwind the recursion of camera.go:327-330 from the terminal radiance
                 L = unwind_clamp(T, zinfo, L, rstack, sp, cam.max_contribution);
             }
-            if (my_parity == 0u) acc0 = acc0 + L; else acc1 = acc1 + L;
+            { const f3 Z = mk3(0, 0, 0); acc0 = acc0 + (my_parity == 0u ? L : Z); acc1 = acc1 + (my_parity == 0u ? Z : L); }
             active = false;
         }
     }
