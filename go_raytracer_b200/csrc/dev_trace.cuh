@@ -404,6 +404,29 @@ __device__ bool closest_hit(const SceneView& sv, uint32_t root, const RayD& r, f
 
     while (sp > 0) {
         uint32_t ref = stack[--sp];
+        if (FEAT & F_NODE) {
+            // walk down through inner nodes first ("while-while" traversal): the lanes of a warp do their box tests
+            // together and reach their leaves together, instead of alternating box and primitive tests lane by lane
+            while (GRT_REF_TYPE(ref) == GRT_REF_NODE) {
+                const uint32_t ni = ref & GRT_REF_MASK;
+                const float4 n0 = nodes[2 * ni], n1 = nodes[2 * ni + 1];
+                if (STATS) tc->box++;
+                if (!box_hit(n0, n1, r, tmin, tmax)) {
+                    if (sp == 0) { ref = GRT_MAKE_REF(GRT_REF_NONE, 0); break; }
+                    ref = stack[--sp];
+                    continue;
+                }
+                uint32_t l = __float_as_uint(n1.z), rr = __float_as_uint(n1.w);
+                const uint32_t hint = (l >> 31) | ((rr >> 31) << 1);   // 0: reference order; 1..3: split axis + 1
+                l &= ~GRT_NODE_HINT_BIT; rr &= ~GRT_NODE_HINT_BIT;
+                if (hint) {
+                    const float da = hint == 1u ? r.d.x : (hint == 2u ? r.d.y : r.d.z);
+                    if (da < 0.0f) { const uint32_t tmp = l; l = rr; rr = tmp; }   // the far child waits on the stack
+                }
+                stack[sp++] = rr;
+                ref = l;
+            }
+        }
         uint32_t type = GRT_REF_TYPE(ref);
         uint32_t idx = ref & GRT_REF_MASK;
         if ((FEAT & F_LIST) && type == GRT_REF_LIST) {
@@ -422,17 +445,8 @@ __device__ bool closest_hit(const SceneView& sv, uint32_t root, const RayD& r, f
             }
             type = GRT_REF_TYPE(ref);
             idx = ref & GRT_REF_MASK;
-            if (type == GRT_REF_LIST) { stack[sp++] = ref; continue; }   // nested list
+            if (type == GRT_REF_LIST || type == GRT_REF_NODE) { stack[sp++] = ref; continue; }   // nested list / a BVH inside a list: next pop
             if (type == GRT_REF_NONE) continue;
-        }
-        if ((FEAT & F_NODE) && type == GRT_REF_NODE) {
-            float4 n0 = nodes[2 * idx], n1 = nodes[2 * idx + 1];
-            if (STATS) tc->box++;
-            if (!box_hit(n0, n1, r, tmin, tmax)) continue;
-            uint32_t l = __float_as_uint(n1.z), rr = __float_as_uint(n1.w);
-            stack[sp++] = rr;
-            stack[sp++] = l;
-            continue;
         }
         if (!BOUNDARY && (FEAT & F_MEDIUM) && type == GRT_REF_MEDIUM) {
             // constantMedium.Hit, medium.go:27-58

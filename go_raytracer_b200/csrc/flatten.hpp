@@ -125,6 +125,7 @@ struct FlattenOptions {
     int collapse_whole = 32;   // a BuildBVH result with at most this many leaves becomes one list
     int collapse_leaf = 4;     // inside larger trees, subtrees with at most this many leaves become lists
     bool box_prims = true;     // NewBox results are found with one slab test (GrtBox) instead of six quad tests
+    bool order_hints = true;   // nodes carry the split axis so a ray may visit the nearer child first
 };
 
 class Flattener {
@@ -159,7 +160,7 @@ class Flattener {
     int mediumNeed = 0;
 
     // ---- BuildBVH topology in object space (bvh.go:35-61) ---------------
-    struct BuildNode { int left, right; bool leftIsNode, rightIsNode; int leaves; };  // child: build-node index or hittable id
+    struct BuildNode { int left, right; bool leftIsNode, rightIsNode; int leaves; int axis; };  // child: build-node index or hittable id
     struct Topology { std::vector<BuildNode> nodes; int root = -1; };
 
     bool isBoxPrim(int listPayload) const {
@@ -265,6 +266,7 @@ class Flattener {
         int axis = longestAxis(bb);
         size_t span = end - start;
         BuildNode n;
+        n.axis = -1;   // only a sorted split (span >= 3) orders its children along `axis`
         if (span == 1) { n.left = n.right = objs[start]; n.leftIsNode = n.rightIsNode = false; n.leaves = leafCount(objs[start]); }
         else if (span == 2) { n.left = objs[start]; n.right = objs[start + 1]; n.leftIsNode = n.rightIsNode = false; n.leaves = leafCount(objs[start]) + leafCount(objs[start + 1]); }
         else {
@@ -279,6 +281,7 @@ class Flattener {
             n.left = buildRange(T, objs, start, mid);
             n.right = buildRange(T, objs, mid, end);
             n.leftIsNode = n.rightIsNode = true;
+            n.axis = axis;
             n.leaves = T.nodes[n.left].leaves + T.nodes[n.right].leaves;
         }
         T.nodes.push_back(n);
@@ -301,7 +304,7 @@ class Flattener {
         void add(V3 p) { double v[3] = {p.x, p.y, p.z}; for (int a = 0; a < 3; a++) { lo[a] = std::fmin(lo[a], v[a]); hi[a] = std::fmax(hi[a], v[a]); } }
         void add(const WBox& b) { for (int a = 0; a < 3; a++) { lo[a] = std::fmin(lo[a], b.lo[a]); hi[a] = std::fmax(hi[a], b.hi[a]); } }
     };
-    struct Emitted { uint32_t ref; WBox box; int need; bool spliceable = false; uint32_t list_first = 0, list_count = 0; };
+    struct Emitted { uint32_t ref; WBox box; int need; bool spliceable = false; uint32_t list_first = 0, list_count = 0; bool has_medium = false; };
 
     static float roundDown(double x) {
         if (x == -kInf) return -std::numeric_limits<float>::infinity();
@@ -337,6 +340,7 @@ class Flattener {
         int need = 0;
         for (size_t i = 0; i < ch.size(); i++) {
             e.box.add(ch[i].box);
+            e.has_medium = e.has_medium || ch[i].has_medium;
             uint32_t r = ch[i].ref;
             if (GRT_REF_TYPE(r) == GRT_REF_NONE) continue;
             if (GRT_REF_TYPE(r) == GRT_REF_LIST && ch[i].spliceable) {
@@ -387,6 +391,13 @@ class Flattener {
         n.left = l.ref;
         n.right = r.ref;
         Emitted e;
+        e.has_medium = l.has_medium || r.has_medium;
+        // traversal hint (include/grt.h): only for an unrotated split with no medium below it
+        if (opt.order_hints && bn.axis >= 0 && !e.has_medium && X.c == 1 && X.s == 0) {
+            uint32_t h = (uint32_t)bn.axis + 1u;
+            if (h & 1u) n.left |= GRT_NODE_HINT_BIT;
+            if (h & 2u) n.right |= GRT_NODE_HINT_BIT;
+        }
         e.ref = GRT_MAKE_REF(GRT_REF_NODE, idx);
         e.box = wb;
         e.need = std::max(2, std::max(1 + l.need, r.need));
@@ -532,6 +543,7 @@ class Flattener {
                 F->media.push_back(m);
                 e.ref = GRT_MAKE_REF(GRT_REF_MEDIUM, F->media.size() - 1);
                 e.box = b.box;
+                e.has_medium = true;
                 mediumNeed = std::max(mediumNeed, b.need + 1);
                 break;
             }

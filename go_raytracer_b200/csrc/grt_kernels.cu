@@ -383,7 +383,7 @@ static int validate_scene(const GrtScene* s) {
     };
     if (!check_ref(s->root)) { grt_set_error("scene root ref out of range"); return GRT_E_INVALID; }
     for (uint32_t i = 0; i < s->n_nodes; i++)
-        if (!check_ref(s->nodes[i].left) || !check_ref(s->nodes[i].right)) { grt_set_error("BVH node child ref out of range"); return GRT_E_INVALID; }
+        if (!check_ref(s->nodes[i].left & ~GRT_NODE_HINT_BIT) || !check_ref(s->nodes[i].right & ~GRT_NODE_HINT_BIT)) { grt_set_error("BVH node child ref out of range"); return GRT_E_INVALID; }
     for (uint32_t i = 0; i < s->n_items; i++)
         if (!check_ref(s->items[i] & ~GRT_LIST_LAST)) { grt_set_error("list item ref out of range"); return GRT_E_INVALID; }
     if (s->n_items && !(s->items[s->n_items - 1] & GRT_LIST_LAST)) { grt_set_error("items[] does not end with GRT_LIST_LAST"); return GRT_E_INVALID; }

@@ -123,7 +123,7 @@ int grt_host_flatten_opts(GrtHostScene* s, int collapse_whole, int collapse_leaf
     s->flat.reset(new grt::flat::FlatScene());
     grt::flat::FlattenOptions fo;
     fo.collapse_whole = collapse_whole < 0 ? 0 : collapse_whole; fo.collapse_leaf = collapse_leaf;
-    if (collapse_whole == 0 && collapse_leaf == 0) fo.box_prims = false;   // (0, 0): the reference's tree, node for node
+    if (collapse_whole == 0 && collapse_leaf == 0) { fo.box_prims = false; fo.order_hints = false; }   // (0, 0): the reference's tree, node for node
     grt::flat::Flattener f(s->ir, fo);
     if (!f.run(*s->flat)) { s->flat.reset(); return fail(f.error); }
     *out = s->flat->view();

@@ -66,7 +66,13 @@ extern "C" {
  * visits them, bvh.go:69-82).  Boxes are the reference's fp64 boxes rounded
  * OUTWARD to fp32, so the fp32 slab test never rejects a box the fp64 test
  * accepts.  Children may be nodes or primitives; primitives are not box-tested
- * (bvh.go:73,79 call child.Hit directly). */
+ * (bvh.go:73,79 call child.Hit directly).
+ * Bit 31 of `left` and of `right` together form a 2-bit traversal hint h = left>>31 | (right>>31)<<1:
+ * h = 0: visit left then right, always (the reference's order; required when the subtree holds a
+ * constantMedium, whose random draw makes the visiting order observable); h = 1..3: the children were
+ * split along axis h-1 with `left` on the low side, so a ray with a negative direction component on that
+ * axis may visit `right` first (closest hits are order-independent up to exact ties). */
+#define GRT_NODE_HINT_BIT 0x80000000u
 typedef struct GrtNode {
     float    bmin[3];
     float    bmax[3];

@@ -54,7 +54,7 @@ class FlatInterp:
                         t0, t1 = t1, t0
                     lo, hi = max(lo, t0), min(hi, t1)
                 if ok and hi > lo:
-                    stack.append(int(n["right"])); stack.append(int(n["left"]))
+                    stack.append(int(n["right"]) & 0x7FFFFFFF); stack.append(int(n["left"]) & 0x7FFFFFFF)   # bit 31: order hint
             elif t == N.REF_BOX:      # the six quads of a NewBox, in order
                 fq = int(self.boxes[i]["first_quad"])
                 for f in range(5, -1, -1):
@@ -152,7 +152,7 @@ def test_collapse_options_do_not_change_topology_semantics():
     assert f1.n_nodes > 50
     for i, n in enumerate(nodes):
         if (n["left"] >> 28) & 7 == N.REF_NODE:
-            assert (n["left"] & N.REF_MASK) == i + 1
+            assert (n["left"] & N.REF_MASK) == i + 1          # (bit 31 is the traversal hint)
         assert (n["bmin"] < n["bmax"]).all()
 
 
