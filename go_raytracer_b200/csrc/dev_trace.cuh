@@ -52,6 +52,7 @@ struct DLight { float4 plane, A, B, Qa, U, V; };   // Qa.w = area
 struct DevScene {
     const unsigned char* blob;   // HBM copy of the blob
     uint32_t blob_bytes;
+    uint32_t stage_bytes;        // prefix of the blob every block copies to shared memory: all of it, the hot arrays only, or 0
     uint32_t off_nodes, off_spheres, off_quads, off_quads_cold, off_boxes, off_items, off_media, off_materials, off_textures, off_lights, off_dlights, off_images;
     uint32_t n_nodes, n_spheres, n_quads, n_boxes, n_items, n_media, n_materials, n_textures, n_lights, n_images;
     const GrtTri* tris;          // HBM
@@ -64,31 +65,47 @@ struct DevScene {
 };
 
 // View over either the shared-memory or the HBM copy of the blob.
+// The blob is laid out hot arrays first (nodes, spheres, quad test records, boxes, list entries, media), then the
+// per-hit arrays (quad cold records, materials, textures, lights, images).  `base` serves the hot arrays, `cold`
+// the rest; both point into shared memory when the whole blob is staged.
 struct SceneView {
     const unsigned char* base;
+    const unsigned char* cold;
     const DevScene* ds;
     __device__ __forceinline__ const float4* nodes() const { return (const float4*)(base + ds->off_nodes); }
     __device__ __forceinline__ const GrtSphere* spheres() const { return (const GrtSphere*)(base + ds->off_spheres); }
     __device__ __forceinline__ const DQuadHot* quads() const { return (const DQuadHot*)(base + ds->off_quads); }
-    __device__ __forceinline__ const DQuadCold* quads_cold() const { return (const DQuadCold*)(base + ds->off_quads_cold); }
+    __device__ __forceinline__ const DQuadCold* quads_cold() const { return (const DQuadCold*)(cold + ds->off_quads_cold); }
     __device__ __forceinline__ const GrtBox* boxes() const { return (const GrtBox*)(base + ds->off_boxes); }
     // run-length list entries built at upload: x = first ref (| GRT_LIST_LAST), y = number of consecutive primitives
     __device__ __forceinline__ const uint2* entries() const { return (const uint2*)(base + ds->off_items); }
     __device__ __forceinline__ const GrtMedium* media() const { return (const GrtMedium*)(base + ds->off_media); }
-    __device__ __forceinline__ const GrtMaterial* materials() const { return (const GrtMaterial*)(base + ds->off_materials); }
-    __device__ __forceinline__ const GrtTexture* textures() const { return (const GrtTexture*)(base + ds->off_textures); }
-    __device__ __forceinline__ const GrtLight* lights() const { return (const GrtLight*)(base + ds->off_lights); }
-    __device__ __forceinline__ const DLight* dlights() const { return (const DLight*)(base + ds->off_dlights); }
-    __device__ __forceinline__ const GrtImage* images() const { return (const GrtImage*)(base + ds->off_images); }
+    __device__ __forceinline__ const GrtMaterial* materials() const { return (const GrtMaterial*)(cold + ds->off_materials); }
+    __device__ __forceinline__ const GrtTexture* textures() const { return (const GrtTexture*)(cold + ds->off_textures); }
+    __device__ __forceinline__ const GrtLight* lights() const { return (const GrtLight*)(cold + ds->off_lights); }
+    __device__ __forceinline__ const DLight* dlights() const { return (const DLight*)(cold + ds->off_dlights); }
+    __device__ __forceinline__ const GrtImage* images() const { return (const GrtImage*)(cold + ds->off_images); }
 };
 
-// Cooperative copy of the blob into shared memory (16-byte vectors).
+// Cooperative copy of the staged prefix of the blob into shared memory (16-byte vectors).
 __device__ __forceinline__ void stage_blob(unsigned char* smem, const DevScene& ds) {
     const uint4* src = (const uint4*)ds.blob;
     uint4* dst = (uint4*)smem;
-    uint32_t n = ds.blob_bytes >> 4;
+    uint32_t n = ds.stage_bytes >> 4;
     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = __ldg(src + i);
     __syncthreads();
+}
+
+// STAGED: 0 = read everything from HBM (through L1/L2), 1 = hot arrays in shared memory, 2 = the whole blob in
+// shared memory (then `cold` IS `base`, and costs no register).
+template <int STAGED>
+__device__ __forceinline__ SceneView make_view(const DevScene& ds, unsigned char* smem) {
+    SceneView sv;
+    sv.ds = &ds;
+    if (STAGED) stage_blob(smem, ds);
+    sv.base = STAGED ? smem : ds.blob;
+    sv.cold = STAGED == 2 ? smem : ds.blob;
+    return sv;
 }
 
 struct RayD {

@@ -17,6 +17,6 @@ void grt_set_error(const std::string& s);
 void grt_count_launch(uint64_t n);
 const grtd::DevScene* grt_internal_dev_scene(GrtSceneHandle h);
 int grt_internal_sm_count(GrtSceneHandle h);
-bool grt_internal_staged(GrtSceneHandle h);
+int grt_internal_staged(GrtSceneHandle h);   // 0 none, 1 hot arrays, 2 whole blob
 unsigned int* grt_internal_counter(GrtSceneHandle h);
 int grt_make_dev_camera(const GrtCamera* c, grtd::DevCamera* out);

@@ -46,13 +46,10 @@ void grt_count_launch(uint64_t n) { g_launches += n; }
 // ===========================================================================
 // trace_batch: one thread per ray
 // ===========================================================================
-template <uint32_t FEAT, bool STAGED>
+template <uint32_t FEAT, int STAGED>
 __global__ void __launch_bounds__(128) trace_batch_kernel(const __grid_constant__ DevScene ds, const GrtRay* __restrict__ rays, uint64_t n, GrtHit* __restrict__ hits) {
     extern __shared__ __align__(16) unsigned char smem[];
-    SceneView sv;
-    sv.ds = &ds;
-    if (STAGED) { stage_blob(smem, ds); sv.base = smem; }
-    else sv.base = ds.blob;
+    SceneView sv = make_view<STAGED>(ds, smem);
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float4* rp = (const float4*)(rays + i);
@@ -100,13 +97,10 @@ struct RenderParams {
     GrtStats* stats;
 };
 
-template <uint32_t FEAT, bool STAGED, bool STATS>
+template <uint32_t FEAT, int STAGED, bool STATS>
 __global__ void __launch_bounds__(GRT_MEGA_THREADS, GRT_MEGA_MIN_BLOCKS) render_mega_kernel(const __grid_constant__ RenderParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
-    SceneView sv;
-    sv.ds = &P.scene;
-    if (STAGED) { stage_blob(smem, P.scene); sv.base = smem; }
-    else sv.base = P.scene.blob;
+    SceneView sv = make_view<STAGED>(P.scene, smem);
 
     const unsigned FULL = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31u;
@@ -325,7 +319,7 @@ struct GrtSceneDev {
     void* d_texels = nullptr;
     void* d_perlins = nullptr;
     unsigned int* d_counter = nullptr;
-    bool staged = false;
+    int staged = 0;   // 0 none, 1 hot arrays, 2 whole blob
     int sm_count = 0;
 };
 
@@ -446,7 +440,6 @@ extern "C" int grt_scene_upload(const GrtScene* s, int device, GrtSceneHandle* o
     ds.off_nodes = place(s->n_nodes * (uint32_t)sizeof(GrtNode));
     ds.off_spheres = place(s->n_spheres * (uint32_t)sizeof(GrtSphere));
     ds.off_quads = place(s->n_quads * (uint32_t)sizeof(DQuadHot));
-    ds.off_quads_cold = place(s->n_quads * (uint32_t)sizeof(DQuadCold));
     // run-length list entries (device-internal): consecutive items of one primitive type with
     // consecutive indices collapse into {first ref, count}; LIST refs are remapped to entry indices
     std::vector<uint32_t> item2entry(s->n_items + 1, 0);
@@ -483,6 +476,8 @@ extern "C" int grt_scene_upload(const GrtScene* s, int device, GrtSceneHandle* o
     ds.off_boxes = place(s->n_boxes * (uint32_t)sizeof(GrtBox));
     ds.off_items = place(n_entries * 8u);
     ds.off_media = place(s->n_media * (uint32_t)sizeof(GrtMedium));
+    const uint32_t hot_end = off;   // everything above is read inside the traversal loop
+    ds.off_quads_cold = place(s->n_quads * (uint32_t)sizeof(DQuadCold));
     ds.off_materials = place(s->n_materials * (uint32_t)sizeof(GrtMaterial));
     ds.off_textures = place(s->n_textures * (uint32_t)sizeof(GrtTexture));
     ds.off_lights = place(s->n_lights * (uint32_t)sizeof(GrtLight));
@@ -545,6 +540,7 @@ extern "C" int grt_scene_upload(const GrtScene* s, int device, GrtSceneHandle* o
     }
     put(ds.off_images, s->images, s->n_images * sizeof(GrtImage));
     ds.blob_bytes = off;
+    ds.stage_bytes = off <= GRT_STAGE_MAX_BYTES ? off : (hot_end <= GRT_STAGE_MAX_BYTES ? hot_end : 0u);
     ds.n_nodes = s->n_nodes; ds.n_spheres = s->n_spheres; ds.n_quads = s->n_quads; ds.n_boxes = s->n_boxes; ds.n_items = n_entries; ds.n_media = s->n_media;
     ds.n_materials = s->n_materials; ds.n_textures = s->n_textures; ds.n_lights = s->n_lights; ds.n_images = s->n_images;
     ds.n_tris = s->n_tris; ds.n_perlins = s->n_perlins;
@@ -570,7 +566,7 @@ extern "C" int grt_scene_upload(const GrtScene* s, int device, GrtSceneHandle* o
     ds.texels = (const uint8_t*)h->d_texels;
     ds.perlins = (const GrtPerlin*)h->d_perlins;
     CUDA_TRY(cudaMalloc((void**)&h->d_counter, 256));
-    h->staged = ds.blob_bytes <= GRT_STAGE_MAX_BYTES;
+    h->staged = ds.stage_bytes == 0 ? 0 : (ds.stage_bytes == ds.blob_bytes ? 2 : 1);
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     h->sm_count = prop.multiProcessorCount;
@@ -588,7 +584,7 @@ extern "C" int grt_scene_free(GrtSceneHandle h) {
 
 const DevScene* grt_internal_dev_scene(GrtSceneHandle h) { return &h->ds; }
 int grt_internal_sm_count(GrtSceneHandle h) { return h->sm_count; }
-bool grt_internal_staged(GrtSceneHandle h) { return h->staged; }
+int grt_internal_staged(GrtSceneHandle h) { return h->staged; }
 unsigned int* grt_internal_counter(GrtSceneHandle h) { return h->d_counter; }
 
 // ---- feature-variant dispatch ------------------------------------------------
@@ -603,11 +599,11 @@ unsigned int* grt_internal_counter(GrtSceneHandle h) { return h->d_counter; }
 template <uint32_t FEAT>
 static int launch_trace(GrtSceneDev* h, const GrtRay* d_rays, uint64_t n, GrtHit* d_hits, cudaStream_t st) {
     unsigned blocks = (unsigned)((n + 127) / 128);
-    if (h->staged) {
-        CUDA_TRY(cudaFuncSetAttribute(trace_batch_kernel<FEAT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->ds.blob_bytes));
-        trace_batch_kernel<FEAT, true><<<blocks, 128, h->ds.blob_bytes, st>>>(h->ds, d_rays, n, d_hits);
-    } else {
-        trace_batch_kernel<FEAT, false><<<blocks, 128, 0, st>>>(h->ds, d_rays, n, d_hits);
+    if (h->staged == 2) {
+        CUDA_TRY(cudaFuncSetAttribute(trace_batch_kernel<FEAT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->ds.stage_bytes));
+        trace_batch_kernel<FEAT, 2><<<blocks, 128, h->ds.stage_bytes, st>>>(h->ds, d_rays, n, d_hits);
+    } else {   // (hot-prefix staging is not worth a third kernel for the one-shot ray query)
+        trace_batch_kernel<FEAT, 0><<<blocks, 128, 0, st>>>(h->ds, d_rays, n, d_hits);
     }
     grt_count_launch(1);
     CUDA_TRY(cudaGetLastError());
@@ -672,14 +668,19 @@ int grt_make_dev_camera(const GrtCamera* c, DevCamera* out) {
 template <uint32_t FEAT>
 static int launch_mega(GrtSceneDev* h, RenderParams& P, bool stats, cudaStream_t st) {
     int blocks = h->sm_count * GRT_MEGA_MIN_BLOCKS;
-    size_t smem = h->staged ? h->ds.blob_bytes : 0;
+    size_t smem = h->staged ? h->ds.stage_bytes : 0;
 #define GRT_LAUNCH(STAGED_, STATS_)                                                                                           \
     do {                                                                                                                      \
         if (smem) CUDA_TRY(cudaFuncSetAttribute(render_mega_kernel<FEAT, STAGED_, STATS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         render_mega_kernel<FEAT, STAGED_, STATS_><<<blocks, GRT_MEGA_THREADS, smem, st>>>(P);                                 \
     } while (0)
-    if (h->staged) { if (stats) GRT_LAUNCH(true, true); else GRT_LAUNCH(true, false); }
-    else { if (stats) GRT_LAUNCH(false, true); else GRT_LAUNCH(false, false); }
+    // quad-only variants are for tiny scenes: whole-blob staging or none (keeps the number of kernels down)
+    constexpr bool tiny = (FEAT & (F_NODE | F_SPHERE | F_TRI)) == 0;
+    int mode = h->staged;
+    if (tiny && mode == 1) { mode = 0; smem = 0; }
+    if (mode == 2) { if (stats) GRT_LAUNCH(2, true); else GRT_LAUNCH(2, false); }
+    else if (mode == 1) { if constexpr (!tiny) { if (stats) GRT_LAUNCH(1, true); else GRT_LAUNCH(1, false); } }
+    else { if (stats) GRT_LAUNCH(0, true); else GRT_LAUNCH(0, false); }
 #undef GRT_LAUNCH
     grt_count_launch(1);
     CUDA_TRY(cudaGetLastError());
@@ -715,6 +716,10 @@ extern "C" int grt_render_device(GrtSceneHandle h, const GrtCamera* cam, const G
     uint32_t claim = (uint32_t)(8192 / (paths_per_pixel ? paths_per_pixel : 1));
     if (claim < 1) claim = 1;
     if (claim > 64) claim = 64;
+    // small images: every resident warp must get several claims, or most of the machine idles
+    uint32_t per_warp = P.n_pixels / ((uint32_t)h->sm_count * GRT_MEGA_MIN_BLOCKS * (GRT_MEGA_THREADS / 32) * 4u);
+    if (per_warp < 1) per_warp = 1;
+    if (claim > per_warp) claim = per_warp;
     P.claim = claim;
     P.rgb_sum = d_rgb_sum;
     P.counter = h->d_counter;

@@ -49,13 +49,8 @@ struct WfParams {
     float* rgb_sum;
 };
 
-__device__ __forceinline__ SceneView wf_view(const WfParams& P, unsigned char* smem, bool staged) {
-    SceneView sv;
-    sv.ds = &P.scene;
-    if (staged) { stage_blob(smem, P.scene); sv.base = smem; }
-    else sv.base = P.scene.blob;
-    return sv;
-}
+template <int STAGED>
+__device__ __forceinline__ SceneView wf_view(const WfParams& P, unsigned char* smem) { return make_view<STAGED>(P.scene, smem); }
 
 // ---- generate ----------------------------------------------------------------------------------
 template <uint32_t FEAT>
@@ -88,10 +83,10 @@ __global__ void __launch_bounds__(256) wf_generate(const __grid_constant__ WfPar
 }
 
 // ---- extend + enqueue ----------------------------------------------------------------------------
-template <uint32_t FEAT, bool STAGED>
+template <uint32_t FEAT, int STAGED>
 __global__ void __launch_bounds__(256) wf_extend(const __grid_constant__ WfParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
-    SceneView sv = wf_view(P, smem, STAGED);
+    SceneView sv = wf_view<STAGED>(P, smem);
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned FULL = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31u;
@@ -144,10 +139,10 @@ __device__ __forceinline__ void wf_finish_path(const WfParams& P, uint32_t slot,
     P.S3[slot].z = WF_FREE;
 }
 
-template <uint32_t FEAT, bool STAGED, int Q>
+template <uint32_t FEAT, int STAGED, int Q>
 __global__ void __launch_bounds__(256) wf_shade(const __grid_constant__ WfParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
-    SceneView sv = wf_view(P, smem, STAGED);
+    SceneView sv = wf_view<STAGED>(P, smem);
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= P.counters[Q]) return;
     const uint32_t slot = P.queues[(size_t)Q * P.P + j];
@@ -222,16 +217,16 @@ __global__ void wf_init_slots(uint4* S3, uint32_t P) {
 template <uint32_t FEAT>
 static int wf_run(GrtSceneHandle h, WfParams& P, cudaStream_t st, uint32_t* h_counters) {
     int rc = GRT_OK;
-    const bool staged = grt_internal_staged(h);
-    const size_t smem = staged ? P.scene.blob_bytes : 0;
+    const bool staged = grt_internal_staged(h) == 2;   // whole-blob staging or none
+    const size_t smem = staged ? P.scene.stage_bytes : 0;
     const unsigned blocks = (P.P + 255) / 256;
     const bool has_spec = (P.scene.features & F_SPECULAR) != 0;
     uint64_t launches = 0;
     if (smem) {
-        cudaFuncSetAttribute(wf_extend<FEAT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(wf_shade<FEAT, true, Q_TERMINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(wf_shade<FEAT, true, Q_DIFFUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(wf_shade<FEAT, true, Q_SPECULAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(wf_extend<FEAT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(wf_shade<FEAT, 2, Q_TERMINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(wf_shade<FEAT, 2, Q_DIFFUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(wf_shade<FEAT, 2, Q_SPECULAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     }
     wf_init_slots<<<blocks, 256, 0, st>>>(P.S3, P.P);
     launches++;
@@ -240,15 +235,15 @@ static int wf_run(GrtSceneHandle h, WfParams& P, cudaStream_t st, uint32_t* h_co
         CU(cudaMemsetAsync(P.counters, 0, C_WORDS * 4, st));
         wf_generate<FEAT><<<blocks, 256, 0, st>>>(P);
         if (staged) {
-            wf_extend<FEAT, true><<<blocks, 256, smem, st>>>(P);
-            wf_shade<FEAT, true, Q_TERMINAL><<<blocks, 256, smem, st>>>(P);
-            wf_shade<FEAT, true, Q_DIFFUSE><<<blocks, 256, smem, st>>>(P);
-            if (has_spec) wf_shade<FEAT, true, Q_SPECULAR><<<blocks, 256, smem, st>>>(P);
+            wf_extend<FEAT, 2><<<blocks, 256, smem, st>>>(P);
+            wf_shade<FEAT, 2, Q_TERMINAL><<<blocks, 256, smem, st>>>(P);
+            wf_shade<FEAT, 2, Q_DIFFUSE><<<blocks, 256, smem, st>>>(P);
+            if (has_spec) wf_shade<FEAT, 2, Q_SPECULAR><<<blocks, 256, smem, st>>>(P);
         } else {
-            wf_extend<FEAT, false><<<blocks, 256, 0, st>>>(P);
-            wf_shade<FEAT, false, Q_TERMINAL><<<blocks, 256, 0, st>>>(P);
-            wf_shade<FEAT, false, Q_DIFFUSE><<<blocks, 256, 0, st>>>(P);
-            if (has_spec) wf_shade<FEAT, false, Q_SPECULAR><<<blocks, 256, 0, st>>>(P);
+            wf_extend<FEAT, 0><<<blocks, 256, 0, st>>>(P);
+            wf_shade<FEAT, 0, Q_TERMINAL><<<blocks, 256, 0, st>>>(P);
+            wf_shade<FEAT, 0, Q_DIFFUSE><<<blocks, 256, 0, st>>>(P);
+            if (has_spec) wf_shade<FEAT, 0, Q_SPECULAR><<<blocks, 256, 0, st>>>(P);
         }
         launches += has_spec ? 5 : 4;
         if ((iter & 7u) == 7u || iter < 2) {   // the host only needs to know when the pool has drained
