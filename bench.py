@@ -245,6 +245,10 @@ def run_ours(args):
         sc2 = g.DeviceScene(s2, local)
         _, _, st = sc2.render(cam2, seed=args.seed, variant=N.GRT_VARIANT_MEGAKERNEL, want_stats=True)   # event counts are variant-independent
         sc2.close()
+        # lane occupancy of the kernel's trace phase at the REAL per-pixel sample count (a centre window is enough)
+        c0 = max(0, cam.width // 2 - 64)
+        _, _, st_occ = scene.render(cam, seed=args.seed, variant=N.GRT_VARIANT_MEGAKERNEL, sample_first=rank, sample_stride=world,
+                                    window=(c0, c0, min(cam.width, c0 + 128), min(cam.height, c0 + 128)), want_stats=True)
         executed = {k: st[k] / st["paths"] for k in COSTS}            # what THIS kernel executes (ordered runs, box slabs, zero-weight cut-off)
         ref_events = dict(ORACLE_EVENTS_PER_PATH)
         ref_src = "frozen (bench.py:ORACLE_EVENTS_PER_PATH)"
@@ -288,7 +292,7 @@ def run_ours(args):
                     "peak_source": f"SMs({props.multi_processor_count}) x 128 lanes x 2 x {sm_mhz:.0f} MHz observed during the run",
                     "flops_per_path": flops_pp, "onchip_bytes_per_path": onchip_bytes_pp, "hbm_bytes_per_path": hbm_bytes_pp,
                     "events_per_path": ref_events, "events_source": ref_src, "executed_events_per_path": executed,
-                    "lanes_per_warp_iteration": st["lane_iterations"] / max(1, st["warp_iterations"]),
+                    "lanes_per_warp_iteration": st_occ["lane_iterations"] / max(1, st_occ["warp_iterations"]),
                     "traffic": traffic,
                     "hbm": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                             "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"},

@@ -42,6 +42,13 @@ class GrtSceneOptions(C.Structure):
                 ("image_rgb", C.c_void_p)]
 
 
+class GrtObjOptions(C.Structure):
+    """objLoader.LoadObjOptions (objLoader.go:17-29)."""
+    _fields_ = [("ScaleFactor", C.c_double), ("FlipYZ", C.c_int32), ("IgnoreNormals", C.c_int32), ("Center", C.c_int32),
+                ("FlipFaces", C.c_int32), ("IgnoreMtl", C.c_int32), ("FindWindows", C.c_int32),
+                ("Position", C.c_double * 3), ("DefaultMaterial", C.c_int32)]
+
+
 class GrtCamera(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("spp_sqrt", C.c_int32), ("max_depth", C.c_int32),
                 ("center", C.c_double * 3), ("pixel00", C.c_double * 3), ("delta_u", C.c_double * 3),
@@ -93,12 +100,15 @@ BOX_DTYPE = np.dtype([("mn", "<f4", 3), ("first_quad", "<u4"), ("mx", "<f4", 3),
                       ("rc", "<f4"), ("rs", "<f4"), ("pad", "<f4", 3)])
 TRI_DTYPE = np.dtype([("v0", "<f4", 3), ("mat", "<u4"), ("e0", "<f4", 3), ("id", "<u4"), ("e1", "<f4", 3),
                       ("flags", "<u4")])
+MATERIAL_DTYPE = np.dtype([("type", "<u4"), ("tex", "<u4"), ("albedo", "<f4", 3), ("fuzz", "<f4"), ("ior", "<f4"), ("pad", "<u4")])
+TEXTURE_DTYPE = np.dtype([("type", "<u4"), ("color", "<f4", 3), ("scale", "<f4"), ("even", "<u4"), ("odd", "<u4"), ("aux", "<u4")])
 RAY_DTYPE = np.dtype([("o", "<f4", 3), ("tmin", "<f4"), ("d", "<f4", 3), ("tmax", "<f4"), ("time", "<f4"),
                       ("self_id", "<u4"), ("pad", "<u4", 2)])
 HIT_DTYPE = np.dtype([("t", "<f4"), ("id", "<u4"), ("ref", "<u4"), ("front_face", "<u4"), ("p", "<f4", 3),
                       ("u", "<f4"), ("n", "<f4", 3), ("v", "<f4")])
 assert NODE_DTYPE.itemsize == 32 and SPHERE_DTYPE.itemsize == 64 and QUAD_DTYPE.itemsize == 96
 assert TRI_DTYPE.itemsize == 48 and RAY_DTYPE.itemsize == 48 and HIT_DTYPE.itemsize == 48
+assert MATERIAL_DTYPE.itemsize == 32 and TEXTURE_DTYPE.itemsize == 32 and BOX_DTYPE.itemsize == 64
 
 _lib = None
 
@@ -137,6 +147,7 @@ def lib():
         "grt_host_translate": (i32, [vp, i32, P(dbl)]), "grt_host_rotate_y": (i32, [vp, i32, dbl]),
         "grt_host_constant_medium": (i32, [vp, i32, dbl, i32]),
         "grt_host_set_world": (i32, [vp, i32]), "grt_host_set_lights": (i32, [vp, i32]),
+        "grt_host_load_obj": (i32, [vp, C.c_char_p, C.c_char_p, P(GrtObjOptions), P(i32), P(i32), P(i32)]),
         "grt_host_builtin_scene": (i32, [vp, i32, P(GrtSceneOptions), P(GrtCameraConfig)]),
         "grt_host_flatten": (i32, [vp, P(GrtScene)]), "grt_host_flatten_opts": (i32, [vp, i32, i32, P(GrtScene)]), "grt_host_camera_derive": (i32, [P(GrtCameraConfig), P(GrtCamera)]),
         "grt_host_write_ppm": (C.c_long, [vp, i32, i32, vp, C.c_long]),
@@ -162,7 +173,7 @@ EXPORTED_SYMBOLS = [
     "grt_host_dielectric", "grt_host_diffuse_light", "grt_host_isotropic", "grt_host_sphere", "grt_host_motion_sphere",
     "grt_host_quad", "grt_host_box", "grt_host_triangle", "grt_host_list", "grt_host_list_add", "grt_host_bvh",
     "grt_host_translate", "grt_host_rotate_y", "grt_host_constant_medium", "grt_host_set_world", "grt_host_set_lights",
-    "grt_host_builtin_scene", "grt_host_flatten", "grt_host_flatten_opts", "grt_host_camera_derive", "grt_host_write_ppm",
+    "grt_host_load_obj", "grt_host_builtin_scene", "grt_host_flatten", "grt_host_flatten_opts", "grt_host_camera_derive", "grt_host_write_ppm",
     "grt_host_camera_render", "grt_host_scene_description",
 ]
 

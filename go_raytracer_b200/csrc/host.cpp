@@ -3,6 +3,7 @@
 #include "scene_ir.hpp"
 #include "scenes.hpp"
 #include "flatten.hpp"
+#include "obj_loader.hpp"
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -80,6 +81,26 @@ int grt_host_constant_medium(GrtHostScene* s, int boundary, double density, int 
 }
 int grt_host_set_world(GrtHostScene* s, int obj) { try { s->ir.checkH(obj); s->ir.world = obj; return 0; } catch (const std::exception& ex) { return fail(ex.what()); } }
 int grt_host_set_lights(GrtHostScene* s, int obj) { try { s->ir.checkH(obj); s->ir.lights = obj; return 0; } catch (const std::exception& ex) { return fail(ex.what()); } }
+
+int grt_host_load_obj(GrtHostScene* s, const char* obj_text, const char* mtl_text, const GrtObjOptions* o,
+                      int* model_out, int* lights_out, int* n_triangles_out) {
+    if (!s || !obj_text) return fail("NULL argument");
+    grt::obj::LoadObjOptions opt;
+    if (o) {
+        opt.ScaleFactor = o->ScaleFactor; opt.FlipYZ = o->FlipYZ != 0; opt.IgnoreNormals = o->IgnoreNormals != 0; opt.Center = o->Center != 0;
+        opt.FlipFaces = o->FlipFaces != 0; opt.IgnoreMtl = o->IgnoreMtl != 0; opt.FindWindows = o->FindWindows != 0;
+        opt.Position = v3(o->Position); opt.DefaultMaterial = o->DefaultMaterial;
+    }
+    grt::obj::LoadResult lr;
+    std::string err;
+    try {
+        if (!grt::obj::loadObj(s->ir, obj_text, mtl_text ? mtl_text : "", opt, lr, err)) return fail(err);
+    } catch (const std::exception& ex) { return fail(ex.what()); }
+    if (model_out) *model_out = lr.model;
+    if (lights_out) *lights_out = lr.lights;
+    if (n_triangles_out) *n_triangles_out = lr.nTriangles;
+    return 0;
+}
 
 static void toC(const grt::ir::CameraConfig& c, GrtCameraConfig* o) {
     o->AspectRatio = c.AspectRatio; o->Width = c.Width; o->SamplesPerPixel = c.SamplesPerPixel; o->MaxDepth = c.MaxDepth; o->MaxThreads = c.MaxThreads;

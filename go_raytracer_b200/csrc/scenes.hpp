@@ -7,6 +7,7 @@
 // reference's draw ORDER.
 #pragma once
 #include "scene_ir.hpp"
+#include "obj_loader.hpp"
 #include <cstdio>
 
 namespace grt {
@@ -322,67 +323,44 @@ inline void cornellSmoke(Scene& s, CameraConfig& c, const SceneOptions& o) {
     applyOverrides(c, o);
 }
 
-// Synthetic mesh for config C5: UV sphere of nseg x nseg
-// segments with radius 1 + 0.08 sin(7θ) sin(5φ) + 0.02 sin(31θ+17φ), smooth
-// vertex normals, run through the objLoader's vertex pipeline
-// (objLoader.go:188-251: scale, bounds, centre, position) and its triangle
-// construction (NewTriangleWithNormals for `f a//na b//nb c//nc`, :440-452).
-// Returns the model list id (the caller wraps it in BuildBVH like :512).
-inline int displacedSphereMesh(Scene& s, int nseg, double scale, V3 position, int mat) {
+// Synthetic mesh for config C5 as OBJ TEXT: a UV sphere of nseg x nseg quad faces with radius
+// 1 + 0.08 sin(7θ) sin(5φ) + 0.02 sin(31θ+17φ) and smooth vertex normals (`v`, `vn`, `f a//a b//b d//d c//c`),
+// deterministic, no RNG.  It is then loaded through the objLoader mirror (obj_loader.hpp) exactly like
+// modelExample loads dragon.obj: ScaleFactor 5, Center, Position (main.go:377-383), fan triangulation
+// (objLoader.go:396-467), NewTriangleWithNormals.  %.17g keeps every double exact through the text.
+inline std::string displacedSphereObj(int nseg) {
     const double PI = 3.14159265358979323846;
-    int nv = (nseg + 1) * (nseg + 1);
-    std::vector<V3> raw(nv), nrm(nv);
-    auto radius = [&](double th, double ph) {
-        return 1.0 + 0.08 * std::sin(7 * th) * std::sin(5 * ph) + 0.02 * std::sin(31 * th + 17 * ph);
-    };
+    auto radius = [&](double th, double ph) { return 1.0 + 0.08 * std::sin(7 * th) * std::sin(5 * ph) + 0.02 * std::sin(31 * th + 17 * ph); };
     auto pos = [&](double th, double ph) {
         double r = radius(th, ph);
         return V3(r * std::sin(th) * std::cos(ph), r * std::cos(th), r * std::sin(th) * std::sin(ph));
     };
-    double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+    std::string out;
+    out.reserve((size_t)(nseg + 1) * (nseg + 1) * 140 + (size_t)nseg * nseg * 60);
+    out += "# displaced UV sphere, generated (SURVEY.md 8d, config C5)\n";
+    char buf[256];
     for (int i = 0; i <= nseg; i++) {
         for (int j = 0; j <= nseg; j++) {
             double th = PI * (double)i / nseg, ph = 2 * PI * (double)j / nseg;
-            V3 p = pos(th, ph) * scale;
-            raw[i * (nseg + 1) + j] = p;
-            mn[0] = std::fmin(mn[0], p.x); mn[1] = std::fmin(mn[1], p.y); mn[2] = std::fmin(mn[2], p.z);
-            mx[0] = std::fmax(mx[0], p.x); mx[1] = std::fmax(mx[1], p.y); mx[2] = std::fmax(mx[2], p.z);
-            // smooth normal from central differences of the displaced surface
-            double e = 1e-4;
-            V3 a = pos(th + e, ph) - pos(th - e, ph);
-            V3 b = pos(th, ph + e) - pos(th, ph - e);
+            V3 p = pos(th, ph);
+            double e = 1e-4;   // smooth normal from central differences of the displaced surface, oriented outward
+            V3 a = pos(th + e, ph) - pos(th - e, ph), b = pos(th, ph + e) - pos(th, ph - e);
             V3 n(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
             double len = std::sqrt(n.x * n.x + n.y * n.y + n.z * n.z);
-            if (len < 1e-12 || i == 0 || i == nseg) { V3 q = pos(th, ph); len = std::sqrt(q.x * q.x + q.y * q.y + q.z * q.z); n = q; }
-            else {
-                // orient outward
-                V3 q = pos(th, ph);
-                if (n.x * q.x + n.y * q.y + n.z * q.z < 0) n = ir::neg(n);
-            }
-            nrm[i * (nseg + 1) + j] = n * (1.0 / len);
+            if (len < 1e-12 || i == 0 || i == nseg) n = p;
+            else if (n.x * p.x + n.y * p.y + n.z * p.z < 0) n = ir::neg(n);
+            snprintf(buf, sizeof(buf), "v %.17g %.17g %.17g\nvn %.17g %.17g %.17g\n", p.x, p.y, p.z, n.x, n.y, n.z);
+            out += buf;
         }
     }
-    V3 center((mn[0] + mx[0]) / 2, (mn[1] + mx[1]) / 2, (mn[2] + mx[2]) / 2);
-    std::vector<V3> vtx(nv);
-    for (int k = 0; k < nv; k++) vtx[k] = raw[k] + ir::neg(center) + position;
-    int model = s.NewHittableList();
     for (int i = 0; i < nseg; i++) {
         for (int j = 0; j < nseg; j++) {
-            int a = i * (nseg + 1) + j, b = a + 1, cidx = a + (nseg + 1), d = cidx + 1;
-            // quad face a,b,d,c fan-triangulated like objLoader.go:396-398
-            int f[4] = {a, b, d, cidx};
-            for (int k = 2; k < 4; k++) {
-                V3 v[3] = {vtx[f[0]], vtx[f[k - 1]], vtx[f[k]]};
-                V3 n[3] = {nrm[f[0]], nrm[f[k - 1]], nrm[f[k]]};
-                // skip the degenerate triangles at the poles
-                V3 e0 = v[1] - v[0], e1 = v[2] - v[0];
-                V3 cr(e0.y * e1.z - e0.z * e1.y, e0.z * e1.x - e0.x * e1.z, e0.x * e1.y - e0.y * e1.x);
-                if (cr.x * cr.x + cr.y * cr.y + cr.z * cr.z < 1e-24) continue;
-                s.Add(model, s.NewTriangleWithNormals(v, n, mat));
-            }
+            int a = i * (nseg + 1) + j + 1, b = a + 1, c = a + (nseg + 1), d = c + 1;   // OBJ indices are 1-based
+            snprintf(buf, sizeof(buf), "f %d//%d %d//%d %d//%d %d//%d\n", a, a, b, b, d, d, c, c);
+            out += buf;
         }
     }
-    return model;
+    return out;
 }
 
 // main.go:371-409 with the dragon replaced by the synthetic mesh.
@@ -391,9 +369,16 @@ inline void modelExample(Scene& s, CameraConfig& c, const SceneOptions& o) {
     s.Add(world, s.NewSphere(V3(0, -1000, 0), 1000, s.NewLambertian(V3(.4, .4, .4))));
     int gold = s.NewMetal(V3(255.0 / 255.0, 215.0 / 255.0, 0), 0.5);
     int nseg = o.mesh_segments > 0 ? o.mesh_segments : 708;
-    int model = displacedSphereMesh(s, nseg, 5.0, V3(0, 1.8, 0), gold);
-    int lights = s.NewHittableList();  // no emissive triangles in the mesh (objLoader.go:492-510)
-    s.Add(world, s.RotateY(s.BuildBVH(model), 180));
+    obj::LoadObjOptions opt;              // objLoader.DefaultLoadOptions(), then main.go:378-382
+    opt.ScaleFactor = 5;
+    opt.Center = true;
+    opt.Position = V3(0, 1.8, 0);
+    opt.DefaultMaterial = gold;
+    obj::LoadResult lr;
+    std::string err;
+    if (!obj::loadObj(s, displacedSphereObj(nseg), std::string(), opt, lr, err)) throw std::runtime_error(err);
+    int lights = lr.lights;               // no emissive triangles in this mesh (objLoader.go:492-510)
+    s.Add(world, s.RotateY(lr.model, 180));
     int light = s.NewSphere(V3(7, 13, 7), 5, s.NewDiffuseLight(V3(4, 4, 4)));
     s.Add(world, light);
     s.Add(lights, light);

@@ -134,6 +134,20 @@ class Scene:
     def ConstantMedium(self, boundary, density, albedo):
         return self.ConstantMediumTexture(boundary, density, self.NewSolidColor(albedo))
 
+    def LoadObjWithOptions(self, obj_text, mtl_text=None, ScaleFactor=1.0, FlipYZ=False, IgnoreNormals=False, Center=True,
+                           FlipFaces=False, Position=(0, 0, 0), DefaultMaterial=-1, IgnoreMtl=False, FindWindows=False):
+        """objLoader.LoadObjWithOptions on text (objLoader.go:72).  Returns (model BVH, lights list, n triangles)."""
+        o = N.GrtObjOptions()
+        o.ScaleFactor = float(ScaleFactor)
+        o.FlipYZ, o.IgnoreNormals, o.Center, o.FlipFaces = int(FlipYZ), int(IgnoreNormals), int(Center), int(FlipFaces)
+        o.IgnoreMtl, o.FindWindows, o.DefaultMaterial = int(IgnoreMtl), int(FindWindows), int(DefaultMaterial)
+        for i in range(3):
+            o.Position[i] = float(Position[i])
+        model, lights, ntri = C.c_int(-1), C.c_int(-1), C.c_int(0)
+        N.host_check(self._L.grt_host_load_obj(self._h, obj_text.encode(), mtl_text.encode() if mtl_text else None, C.byref(o),
+                                               C.byref(model), C.byref(lights), C.byref(ntri)))
+        return model.value, lights.value, ntri.value
+
     def set_world(self, obj):
         N.host_check(self._L.grt_host_set_world(self._h, obj))
         self.world = obj

@@ -69,6 +69,19 @@ int grt_host_constant_medium(GrtHostScene* s, int boundary, double density, int 
 int grt_host_set_world(GrtHostScene* s, int obj);                                        /* Render's `world`         */
 int grt_host_set_lights(GrtHostScene* s, int obj);                                       /* Render's `lights`        */
 
+/* internal/objLoader: LoadObjWithOptions on in-memory text (objLoader.go:72; mtl_text may be NULL/empty).
+ * model_out receives the BVH over the triangles, lights_out the list of emissive triangles (objLoader.go:489-512).
+ * default_mat < 0: Lambertian(0.8).  Image maps (map_Kd/map_Ka) are not resolved here: a material that needs one
+ * makes the load fail, as a missing file does in the reference. */
+typedef struct GrtObjOptions {
+    double  ScaleFactor;
+    int32_t FlipYZ, IgnoreNormals, Center, FlipFaces, IgnoreMtl, FindWindows;
+    double  Position[3];
+    int32_t DefaultMaterial;
+} GrtObjOptions;
+int grt_host_load_obj(GrtHostScene* s, const char* obj_text, const char* mtl_text, const GrtObjOptions* opt,
+                      int* model_out, int* lights_out, int* n_triangles_out);
+
 /* main.go's scene functions, -S 1..8 (main.go:449-476); fills *cam like the scene function does. */
 int grt_host_builtin_scene(GrtHostScene* s, int scene_id, const GrtSceneOptions* opt, GrtCameraConfig* cam);
 
