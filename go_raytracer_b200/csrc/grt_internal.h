@@ -9,7 +9,9 @@
 #define GRT_MEGA_MIN_BLOCKS 6   /* 80 registers, 24 warps/SM: measured best of 4/5/6 (profiles/README.md) */
 #endif
 // the scene blob is staged into shared memory when every resident block can hold a copy
-#define GRT_STAGE_MAX_BYTES (36u * 1024u)
+#define GRT_STAGE_MAX_BYTES (28u * 1024u)
+// clamp-stack entries per thread kept in shared memory (16 B each)
+#define GRT_RS_SMEM 4
 
 namespace grtd { struct DevScene; struct DevCamera; }
 

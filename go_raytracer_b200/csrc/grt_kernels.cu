@@ -160,7 +160,17 @@ __global__ void __launch_bounds__(GRT_MEGA_THREADS, GRT_MEGA_MIN_BLOCKS) render_
     f3 T = mk3(1, 1, 1);
     uint32_t zinfo = 0;
     int sp = 0;
-    float4 rstack[WEIGHT_STACK];
+    // the first GRT_RS_SMEM entries live in shared memory (one column per thread, conflict-free); deeper entries —
+    // rare — in local memory.  Keeping the hot entries out of local memory matters: 113 664 resident threads x a
+    // 1 KB frame does not fit the L2, and the write-backs showed up as 11 GB/s of DRAM writes (profiles/README.md).
+    __shared__ float4 rs_smem[GRT_RS_SMEM][GRT_MEGA_THREADS];
+    float4 rs_deep[WEIGHT_STACK - GRT_RS_SMEM];
+    struct ClampStack {
+        float4* sm; float4* deep;
+        __device__ __forceinline__ float4 operator[](size_t i) const { return i < GRT_RS_SMEM ? sm[i * GRT_MEGA_THREADS] : deep[i - GRT_RS_SMEM]; }
+        __device__ __forceinline__ void put(int i, float4 v) { if (i < GRT_RS_SMEM) sm[i * GRT_MEGA_THREADS] = v; else deep[i - GRT_RS_SMEM] = v; }
+    } rstack;
+    rstack.sm = &rs_smem[0][threadIdx.x]; rstack.deep = rs_deep;
     // stats
     uint32_t st_paths = 0, st_segments = 0, st_diffuse = 0, st_specular = 0, st_lightpdf = 0, st_nan = 0, st_iters = 0;
     TraceCounters tc;
@@ -254,7 +264,7 @@ __global__ void __launch_bounds__(GRT_MEGA_THREADS, GRT_MEGA_MIN_BLOCKS) render_
                     if (R.value.x == 0.0f && R.value.y == 0.0f && R.value.z == 0.0f) { terminate = true; }  // weight 0: the sample is 0 whatever follows
                     else {
                         // 1/T_before_j; a zero component stays zero in P0 as well, so its reciprocal is irrelevant
-                        rstack[sp++] = recip_factor(T);
+                        rstack.put(sp++, recip_factor(T));
                         apply_factor(T, zinfo, R.value, sp);
                     }
                 }
