@@ -6,6 +6,7 @@
 // (sphere.Hit), :167-206 (quad.Hit, isInterior), :408-461 (Triangle.Hit),
 // medium.go:27-58 (constantMedium.Hit).
 #pragma once
+#include "grt_internal.h"
 #include "dev_math.cuh"
 #include "../../include/grt.h"
 
@@ -140,11 +141,10 @@ struct TraceCounters {
 // 1/d < 0, shrink, reject when max <= min.  fminf/fmaxf drop NaN where Go's
 // min/max propagate it; the difference only makes Go accept boxes that are
 // geometrically missed, never changes a closest hit.
-__device__ __forceinline__ bool box_hit(float4 n0, float4 n1, const RayD& r, float tmin, float tmax) {
-    // n0 = bmin.xyz, bmax.x ; n1 = bmax.yz, left, right
-    float t0x = (n0.x - r.o.x) * r.invd.x, t1x = (n0.w - r.o.x) * r.invd.x;
-    float t0y = (n0.y - r.o.y) * r.invd.y, t1y = (n1.x - r.o.y) * r.invd.y;
-    float t0z = (n0.z - r.o.z) * r.invd.z, t1z = (n1.y - r.o.z) * r.invd.z;
+__device__ __forceinline__ bool box_hit(float lx, float ly, float lz, float hx, float hy, float hz, const RayD& r, float tmin, float tmax) {
+    float t0x = (lx - r.o.x) * r.invd.x, t1x = (hx - r.o.x) * r.invd.x;
+    float t0y = (ly - r.o.y) * r.invd.y, t1y = (hy - r.o.y) * r.invd.y;
+    float t0z = (lz - r.o.z) * r.invd.z, t1z = (hz - r.o.z) * r.invd.z;
     float ax = r.invd.x < 0 ? t1x : t0x, bx = r.invd.x < 0 ? t0x : t1x;
     float ay = r.invd.y < 0 ? t1y : t0y, by = r.invd.y < 0 ? t0y : t1y;
     float az = r.invd.z < 0 ? t1z : t0z, bz = r.invd.z < 0 ? t0z : t1z;
@@ -152,6 +152,13 @@ __device__ __forceinline__ bool box_hit(float4 n0, float4 n1, const RayD& r, flo
     float hi = fminf(fminf(bx, by), fminf(bz, tmax));
     return !(hi <= lo);
 }
+
+// Device BVH node, 64 bytes, built at upload from the ABI's GrtNode array: a node carries the boxes of its TWO
+// children, so one visit is one 64-byte fetch and two independent slab tests, and the dependent chain per tree level
+// is one load instead of two.  A child that is not an inner node (a primitive, list or medium: the reference does
+// not box-test those, bvh.go:73-79) gets the infinite box, i.e. it is always visited while tmax > tmin.
+//   q0 = l.min.xyz, l.max.x   q1 = l.max.yz, r.min.xy   q2 = r.min.z, r.max.xyz   q3 = left, right (bit 31: order hint), 0, 0
+#define GRT_DNODE_F4 4
 
 // ---- sphere.Hit, objects.go:83-115 ----------------------------------------
 // The cancellation-prone sums (c = |oc|^2 - r^2, disc = h^2 - a c) are fp64;
@@ -329,17 +336,47 @@ struct MediumRngCtx {
 // (HittableList, or a collapsed BVH subtree) is scanned in order in a tight
 // loop (hittable.go:129-136); a non-primitive item parks the rest of the list
 // on the stack as a continuation entry, so a long list never overflows it.
+//
+// The traversal is resumable: its whole state (stack, closest candidate so far) lives in a TravState, and
+// trav_run<.., VOTE=true> returns, state intact, once most lanes of the warp are done.  The megakernel uses
+// that on scenes with a real BVH: the lanes whose rays finished go on to shading and their next ray instead
+// of idling until the warp's longest traversal ends (results do not depend on where a traversal is interrupted).
+// STRIDE == 1: the stack is a thread-local array.  STRIDE > 1: the stack is this thread's column of a shared-memory
+// array [STACK][STRIDE] (`ext` points at row 0): a local-memory stack of 113 664 resident threads does not fit the
+// L1/L2, so every pop of a deep traversal was an L2 or DRAM round trip on the critical path.
+template <bool BOUNDARY, int STRIDE = 1>
+struct TravState {
+    static constexpr int STACK = BOUNDARY ? GRT_STACK_BOUNDARY : GRT_STACK_MAIN;
+    static constexpr int NSMEM = STRIDE == 1 ? 0 : GRT_TRAV_SMEM;   // entries held in shared memory; deeper ones overflow
+    uint32_t local[STACK - NSMEM > 0 ? STACK - NSMEM : 1];
+    uint32_t* ext;
+    __device__ __forceinline__ uint32_t& at(int i) { return (STRIDE == 1 || i >= NSMEM) ? local[i - NSMEM] : ext[i * STRIDE]; }
+    int sp;
+    float tmax;          // the closest t so far; plays the role of rayT.Max (bvh.go:78)
+    uint32_t ref;        // the closest primitive so far, GRT_REF_NONE: none
+    float u, v;
+};
+template <typename TS>
+__device__ __forceinline__ void trav_begin(TS& ts, uint32_t root, float tmax) {
+    ts.at(0) = root; ts.sp = 1; ts.tmax = tmax; ts.ref = GRT_MAKE_REF(GRT_REF_NONE, 0); ts.u = 0; ts.v = 0;
+}
+
 template <uint32_t FEAT, bool BOUNDARY, bool STATS>
+__device__ bool closest_hit(const SceneView& sv, uint32_t root, const RayD& r, float tmin, float tmax,
+                            uint32_t self_id, uint32_t self_ref, MediumRngCtx* mrng, HitInfo& hit, TraceCounters* tc);
+
 // Self exclusion: the primitive the ray starts on is named by its object id (`self_id`, the C ABI's
 // notion) and by its flat ref (`self_ref`).  When every object id maps to one flat primitive the cheap
 // ref comparison is used; with F_DUPIDS the id of every candidate is compared.
-__device__ bool closest_hit(const SceneView& sv, uint32_t root, const RayD& r, float tmin, float tmax,
-                            uint32_t self_id, uint32_t self_ref, MediumRngCtx* mrng, HitInfo& hit, TraceCounters* tc) {
-    constexpr int STACK = BOUNDARY ? GRT_STACK_BOUNDARY : GRT_STACK_MAIN;
-    uint32_t stack[STACK];
-    int sp = 0;
-    stack[sp++] = root;
-    hit.ref = GRT_MAKE_REF(GRT_REF_NONE, 0);   // "no hit yet"; the closest t lives in tmax
+// Returns true when the traversal is complete.
+template <uint32_t FEAT, bool BOUNDARY, bool STATS, bool VOTE, typename TS>
+__device__ __forceinline__ bool trav_run(const SceneView& sv, TS& ts, const RayD& r, float tmin,
+                                         uint32_t self_id, uint32_t self_ref, MediumRngCtx* mrng, TraceCounters* tc,
+                                         unsigned mask, int exit16) {
+    int sp = ts.sp;
+    float tmax = ts.tmax;
+    HitInfo hit;
+    hit.ref = ts.ref; hit.u = ts.u; hit.v = ts.v;
     const float4* nodes = sv.nodes();
     const uint32_t excl = BOUNDARY ? GRT_NO_ID : self_id;
     const uint32_t excl_ref = BOUNDARY ? 0xFFFFFFFFu : self_ref;
@@ -419,31 +456,8 @@ __device__ bool closest_hit(const SceneView& sv, uint32_t root, const RayD& r, f
         return type == GRT_REF_QUAD || type == GRT_REF_SPHERE || type == GRT_REF_TRI || type == GRT_REF_BOX || type == GRT_REF_NONE;
     };
 
-    while (sp > 0) {
-        uint32_t ref = stack[--sp];
-        if (FEAT & F_NODE) {
-            // walk down through inner nodes first ("while-while" traversal): the lanes of a warp do their box tests
-            // together and reach their leaves together, instead of alternating box and primitive tests lane by lane
-            while (GRT_REF_TYPE(ref) == GRT_REF_NODE) {
-                const uint32_t ni = ref & GRT_REF_MASK;
-                const float4 n0 = nodes[2 * ni], n1 = nodes[2 * ni + 1];
-                if (STATS) tc->box++;
-                if (!box_hit(n0, n1, r, tmin, tmax)) {
-                    if (sp == 0) { ref = GRT_MAKE_REF(GRT_REF_NONE, 0); break; }
-                    ref = stack[--sp];
-                    continue;
-                }
-                uint32_t l = __float_as_uint(n1.z), rr = __float_as_uint(n1.w);
-                const uint32_t hint = (l >> 31) | ((rr >> 31) << 1);   // 0: reference order; 1..3: split axis + 1
-                l &= ~GRT_NODE_HINT_BIT; rr &= ~GRT_NODE_HINT_BIT;
-                if (hint) {
-                    const float da = hint == 1u ? r.d.x : (hint == 2u ? r.d.y : r.d.z);
-                    if (da < 0.0f) { const uint32_t tmp = l; l = rr; rr = tmp; }   // the far child waits on the stack
-                }
-                stack[sp++] = rr;
-                ref = l;
-            }
-        }
+    // one item that is not an inner node: a list (scanned in order), a medium, or a primitive
+    auto leaf = [&](uint32_t ref) {
         uint32_t type = GRT_REF_TYPE(ref);
         uint32_t idx = ref & GRT_REF_MASK;
         if ((FEAT & F_LIST) && type == GRT_REF_LIST) {
@@ -457,13 +471,13 @@ __device__ bool closest_hit(const SceneView& sv, uint32_t root, const RayD& r, f
                     idx++;
                     continue;
                 }
-                if (!last) stack[sp++] = GRT_MAKE_REF(GRT_REF_LIST, idx + 1);   // the rest of the list, after this item
+                if (!last) ts.at(sp++) = GRT_MAKE_REF(GRT_REF_LIST, idx + 1);   // the rest of the list, after this item
                 break;
             }
             type = GRT_REF_TYPE(ref);
             idx = ref & GRT_REF_MASK;
-            if (type == GRT_REF_LIST || type == GRT_REF_NODE) { stack[sp++] = ref; continue; }   // nested list / a BVH inside a list: next pop
-            if (type == GRT_REF_NONE) continue;
+            if (type == GRT_REF_LIST || type == GRT_REF_NODE) { ts.at(sp++) = ref; return; }   // nested list / a BVH inside a list: next pop
+            if (type == GRT_REF_NONE) return;
         }
         if (!BOUNDARY && (FEAT & F_MEDIUM) && type == GRT_REF_MEDIUM) {
             // constantMedium.Hit, medium.go:27-58
@@ -471,28 +485,108 @@ __device__ bool closest_hit(const SceneView& sv, uint32_t root, const RayD& r, f
             if (STATS) tc->medium++;
             HitInfo h1, h2;
             const float INF = __int_as_float(0x7f800000);
-            if (!closest_hit<FEAT, true, STATS>(sv, m.boundary, r, -INF, INF, GRT_NO_ID, 0xFFFFFFFFu, nullptr, h1, tc)) continue;
-            if (!closest_hit<FEAT, true, STATS>(sv, m.boundary, r, h1.t + 0.0001f, INF, GRT_NO_ID, 0xFFFFFFFFu, nullptr, h2, tc)) continue;
+            if (!closest_hit<FEAT, true, STATS>(sv, m.boundary, r, -INF, INF, GRT_NO_ID, 0xFFFFFFFFu, nullptr, h1, tc)) return;
+            if (!closest_hit<FEAT, true, STATS>(sv, m.boundary, r, h1.t + 0.0001f, INF, GRT_NO_ID, 0xFFFFFFFFu, nullptr, h2, tc)) return;
             float t1 = fmaxf(h1.t, tmin), t2 = fminf(h2.t, tmax);
-            if (t1 >= t2) continue;
+            if (t1 >= t2) return;
             t1 = fmaxf(0.0f, t1);
             float rayLength = sqrtf(len2(r.d));
             float inside = (t2 - t1) * rayLength;
             // medium.go:47 draws only once both boundary hits exist and overlap the interval
             float u = rng_draw(mrng->pixel, mrng->sample, mrng->bounce, GRT_STREAM_MEDIUM, mrng->count++, mrng->k0, mrng->k1);
             float hitDistance = m.neg_inv_density * logf(u);
-            if (hitDistance > inside) continue;
+            if (hitDistance > inside) return;
             float t = t1 + hitDistance / rayLength;
             tmax = t; hit.ref = ref; hit.u = 0; hit.v = 0;
-            continue;
+            return;
         }
         test_prims(ref, 1);   // a primitive that is a direct BVH child (bvh.go:73,79), or NONE
+    };
+    // one inner node: box test, then the near/left child becomes current and the other waits on the stack
+    auto node_step = [&](uint32_t& ref) -> bool {   // false: the stack ran dry
+        const uint32_t ni = ref & GRT_REF_MASK;
+        const float4 q0 = nodes[GRT_DNODE_F4 * ni], q1 = nodes[GRT_DNODE_F4 * ni + 1], q2 = nodes[GRT_DNODE_F4 * ni + 2];
+        const uint2 ch = *(const uint2*)(nodes + GRT_DNODE_F4 * ni + 3);
+        if (STATS) tc->box += 2;
+        bool hl = box_hit(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, r, tmin, tmax);
+        bool hr = box_hit(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, r, tmin, tmax);
+        uint32_t l = ch.x, rr = ch.y;
+        const uint32_t hint = (l >> 31) | ((rr >> 31) << 1);   // 0: reference order; 1..3: split axis + 1
+        l &= ~GRT_NODE_HINT_BIT; rr &= ~GRT_NODE_HINT_BIT;
+        if (hint) {
+            const float da = hint == 1u ? r.d.x : (hint == 2u ? r.d.y : r.d.z);
+            if (da < 0.0f) { const uint32_t tmp = l; l = rr; rr = tmp; const bool tb = hl; hl = hr; hr = tb; }   // the far child waits on the stack
+        }
+        if (hl) {
+            if (hr) ts.at(sp++) = rr;
+            ref = l;
+            return true;
+        }
+        if (hr) { ref = rr; return true; }
+        if (sp == 0) { ref = GRT_MAKE_REF(GRT_REF_NONE, 0); return false; }
+        ref = ts.at(--sp);
+        return true;
+    };
+
+    if (!VOTE) {
+        while (sp > 0) {
+            uint32_t ref = ts.at(--sp);
+            if (FEAT & F_NODE) {
+                // walk down through inner nodes first ("while-while" traversal)
+                while (GRT_REF_TYPE(ref) == GRT_REF_NODE) if (!node_step(ref)) break;
+            }
+            leaf(ref);
+        }
+    } else {
+        // Warp-synchronous traversal.  The lanes in `mask` (they all enter together) vote on every step: while at
+        // least half of the lanes that still have work stand on an inner node, those lanes do one box test each in
+        // lock step; otherwise the lanes standing on a leaf item (list, medium, primitive) process it.  Left to the
+        // compiler's reconvergence the lanes of a warp drift apart and run the loop almost serially (measured:
+        // 5 of 32 lanes active per instruction on the 1M-triangle mesh).  The slice ends for the whole warp once
+        // fewer than exit16/16 of the entering lanes still have work: those keep their state and resume on the
+        // next call, next to lanes that have shaded and started a new segment in the meantime.
+        const uint32_t NONE = GRT_MAKE_REF(GRT_REF_NONE, 0);
+        const int n_enter = __popc(__ballot_sync(mask, sp > 0));
+        uint32_t ref = NONE;
+        if (sp > 0) ref = ts.at(--sp);
+        for (;;) {
+            const bool have = GRT_REF_TYPE(ref) != GRT_REF_NONE;
+            const bool on_node = (FEAT & F_NODE) && GRT_REF_TYPE(ref) == GRT_REF_NODE;
+            const int n_have = __popc(__ballot_sync(mask, have));
+            const int n_node = __popc(__ballot_sync(mask, on_node));
+            if (n_have * 16 < n_enter * exit16 || n_have == 0) break;
+            if (2 * n_node >= n_have) {
+                if (on_node) node_step(ref);
+            } else if (have && !on_node) {
+                leaf(ref);
+                ref = NONE;
+            }
+            if (GRT_REF_TYPE(ref) == GRT_REF_NONE && sp > 0) ref = ts.at(--sp);
+        }
+        if (GRT_REF_TYPE(ref) != GRT_REF_NONE) ts.at(sp++) = ref;
     }
+    ts.sp = sp; ts.tmax = tmax; ts.ref = hit.ref; ts.u = hit.u; ts.v = hit.v;
+    return sp == 0;
+}
+
+// Closes a finished traversal: the winning primitive's t is refined in fp64 where fp32 is not enough.
+template <uint32_t FEAT, typename TS>
+__device__ __forceinline__ bool trav_end(const SceneView& sv, const TS& ts, const RayD& r, HitInfo& hit) {
+    hit.ref = ts.ref; hit.u = ts.u; hit.v = ts.v;
     const bool any = hit.ref != GRT_MAKE_REF(GRT_REF_NONE, 0);
-    hit.t = tmax;
+    hit.t = ts.tmax;
     if ((FEAT & F_ROTQUAD) && any && GRT_REF_TYPE(hit.ref) == GRT_REF_QUAD) hit.t = quad_refine_t(sv.quads_cold() + (hit.ref & GRT_REF_MASK), r, hit.t);
     if ((FEAT & F_TRI) && any && GRT_REF_TYPE(hit.ref) == GRT_REF_TRI && sv.ds->tri_v64) hit.t = tri_refine_t(sv.ds->tri_v64 + 9 * (size_t)(hit.ref & GRT_REF_MASK), r, hit.t);
     return any;
+}
+
+template <uint32_t FEAT, bool BOUNDARY, bool STATS>
+__device__ bool closest_hit(const SceneView& sv, uint32_t root, const RayD& r, float tmin, float tmax,
+                            uint32_t self_id, uint32_t self_ref, MediumRngCtx* mrng, HitInfo& hit, TraceCounters* tc) {
+    TravState<BOUNDARY> ts;
+    trav_begin(ts, root, tmax);
+    trav_run<FEAT, BOUNDARY, STATS, false>(sv, ts, r, tmin, self_id, self_ref, mrng, tc, 0u, 0);
+    return trav_end<FEAT>(sv, ts, r, hit);
 }
 
 // ---- full hit record (HitRecord, hittable.go:14-34) ------------------------

@@ -12,6 +12,20 @@
 #define GRT_STAGE_MAX_BYTES (28u * 1024u)
 // clamp-stack entries per thread kept in shared memory (16 B each)
 #define GRT_RS_SMEM 4
+/* BVH scenes (variants with F_NODE): resident blocks per SM, shared-memory traversal stack entries per thread
+   (deeper entries overflow to local memory), and the staging limit that still lets all blocks fit */
+#ifndef GRT_MEGA_MIN_BLOCKS_BVH
+#define GRT_MEGA_MIN_BLOCKS_BVH 6
+#endif
+#define GRT_TRAV_SMEM 32
+#define GRT_STAGE_MAX_BYTES_BVH (12u * 1024u)
+/* a traversal slice of the megakernel on BVH scenes ends when fewer than GRT_TRAV_EXIT16/16 of the lanes that
+   entered it still have work (env GRT_TRAV_EXIT16 overrides) */
+#define GRT_TRAV_EXIT16 4
+/* non-zero: never use the resumable, warp-synchronous traversal in the megakernel (A/B builds) */
+#ifndef GRT_RESUMABLE_REQ
+#define GRT_RESUMABLE_REQ 0u
+#endif
 
 namespace grtd { struct DevScene; struct DevCamera; }
 

@@ -19,6 +19,7 @@
 #include <mutex>
 #include <algorithm>
 #include <math.h>
+#include <limits>
 
 #include "dev_shade.cuh"
 #include "grt_internal.h"
@@ -92,13 +93,26 @@ struct RenderParams {
     int x0, y0, ww, wh;                            // pixel window
     uint32_t n_pixels;                             // ww * wh
     uint32_t claim;                                // pixels claimed per atomicAdd
+    int trav_exit16;                               // a traversal slice ends when fewer than trav_exit16/16 of its lanes have work left
     float* rgb_sum;                                // device, W*H*3, += per pixel
     unsigned int* counter;
     GrtStats* stats;
 };
 
+// feature-set variants the kernels are instantiated for (a scene runs on the smallest one that covers it)
+#define V_CORNELL (F_QUAD | F_BOX | F_LIST | F_ROTQUAD | F_QUAD_LIGHT)
+#define V_SMOKE (V_CORNELL | F_MEDIUM | F_ISOTROPIC)
+#define V_SPHERES (F_NODE | F_SPHERE | F_LIST | F_SPECULAR | F_TEXTURE | F_SPHERE_LIGHT | F_DEFOCUS)
+#define V_MESH (F_NODE | F_SPHERE | F_TRI | F_LIST | F_SPECULAR | F_SPHERE_LIGHT | F_TRI_LIGHT | F_TRISHADE | F_DEFOCUS)
+#define V_FULL F_ALL
+// The resumable, warp-synchronous traversal pays off where traversal lengths within a warp differ by orders of
+// magnitude (a large mesh next to empty space: +8 % on the 1M-triangle config); on the sphere/box BVHs of the book
+// scenes the plain per-lane loop is faster (profiles/README.md), so only the mesh variant uses it.
+__host__ __device__ constexpr bool mega_resumable(uint32_t feat) { return feat == (V_MESH) && (GRT_RESUMABLE_REQ) == 0u; }
+__host__ __device__ constexpr int mega_min_blocks(uint32_t feat) { return mega_resumable(feat) ? GRT_MEGA_MIN_BLOCKS_BVH : GRT_MEGA_MIN_BLOCKS; }
+
 template <uint32_t FEAT, int STAGED, bool STATS>
-__global__ void __launch_bounds__(GRT_MEGA_THREADS, GRT_MEGA_MIN_BLOCKS) render_mega_kernel(const __grid_constant__ RenderParams P) {
+__global__ void __launch_bounds__(GRT_MEGA_THREADS, mega_min_blocks(FEAT)) render_mega_kernel(const __grid_constant__ RenderParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
     SceneView sv = make_view<STAGED>(P.scene, smem);
 
@@ -171,8 +185,16 @@ __global__ void __launch_bounds__(GRT_MEGA_THREADS, GRT_MEGA_MIN_BLOCKS) render_
         __device__ __forceinline__ void put(int i, float4 v) { if (i < GRT_RS_SMEM) sm[i * GRT_MEGA_THREADS] = v; else deep[i - GRT_RS_SMEM] = v; }
     } rstack;
     rstack.sm = &rs_smem[0][threadIdx.x]; rstack.deep = rs_deep;
+    // resumable traversal state (BVH scenes only)
+    constexpr bool RESUMABLE = mega_resumable(FEAT);
+    __shared__ uint32_t trav_smem[RESUMABLE ? GRT_TRAV_SMEM : 1][RESUMABLE ? GRT_MEGA_THREADS : 1];
+    TravState<false, RESUMABLE ? GRT_MEGA_THREADS : 1> ts;
+    ts.ext = &trav_smem[0][RESUMABLE ? threadIdx.x : 0];
+    ts.sp = 0;
+    bool tracing = false;
+    uint32_t med_count = 0;
     // stats
-    uint32_t st_paths = 0, st_segments = 0, st_diffuse = 0, st_specular = 0, st_lightpdf = 0, st_nan = 0, st_iters = 0;
+    uint32_t st_lane_iters = 0, st_paths = 0, st_segments = 0, st_diffuse = 0, st_specular = 0, st_lightpdf = 0, st_nan = 0, st_iters = 0;
     TraceCounters tc;
     tc.box = tc.sphere = tc.quad = tc.tri = tc.medium = 0;
 
@@ -231,15 +253,29 @@ __global__ void __launch_bounds__(GRT_MEGA_THREADS, GRT_MEGA_MIN_BLOCKS) render_
             continue;
         }
         if (STATS && lane == 0) st_iters++;
-        if (!active) continue;
+        if constexpr (!RESUMABLE) { if (!active) continue; }
+        if (STATS && active) st_lane_iters++;
 
         // ---- one path segment: trace ------------------------------------------
-        if (STATS) st_segments++;
         MediumRngCtx mr;
         mr.pixel = my_pixel_index; mr.sample = my_sample; mr.bounce = (uint32_t)bounce; mr.k0 = P.k0; mr.k1 = P.k1; mr.count = 0;
         HitInfo h;
         const float INF = __int_as_float(0x7f800000);
-        bool hit = closest_hit<FEAT, false, STATS>(sv, P.scene.root, ray, 0.001f, INF, self_id, self_ref, &mr, h, &tc);   // camera.go:300
+        bool hit;
+        if constexpr (RESUMABLE) {
+            // a BVH scene: all 32 lanes run one warp-synchronous traversal slice (idle lanes carry an empty stack), then
+            // the lanes that are done shade and start their next segment while the others resume (dev_trace.cuh)
+            if (active && !tracing) { trav_begin(ts, P.scene.root, INF); tracing = true; med_count = 0; if (STATS) st_segments++; }
+            mr.count = med_count;
+            const bool fin = trav_run<FEAT, false, STATS, true>(sv, ts, ray, 0.001f, self_id, self_ref, &mr, &tc, FULL, P.trav_exit16);
+            med_count = mr.count;
+            if (!active || !fin) continue;
+            tracing = false;
+            hit = trav_end<FEAT>(sv, ts, ray, h);
+        } else {
+            if (STATS) st_segments++;
+            hit = closest_hit<FEAT, false, STATS>(sv, P.scene.root, ray, 0.001f, INF, self_id, self_ref, &mr, h, &tc);   // camera.go:300
+        }
 
         f3 Lterm = mk3(0, 0, 0);
         bool terminate = false, isnan_path = false;
@@ -292,7 +328,7 @@ __global__ void __launch_bounds__(GRT_MEGA_THREADS, GRT_MEGA_MIN_BLOCKS) render_
     }
 
     if (STATS) {
-        unsigned long long v[13] = {st_paths, st_segments, tc.box, tc.sphere, tc.quad, tc.tri, tc.medium, st_diffuse, st_specular, st_lightpdf, st_nan, st_iters, st_segments};
+        unsigned long long v[13] = {st_paths, st_segments, tc.box, tc.sphere, tc.quad, tc.tri, tc.medium, st_diffuse, st_specular, st_lightpdf, st_nan, st_iters, st_lane_iters};
         unsigned long long* dst = (unsigned long long*)P.stats;
 #pragma unroll
         for (int i = 0; i < 13; i++) {
@@ -447,7 +483,7 @@ extern "C" int grt_scene_upload(const GrtScene* s, int device, GrtSceneHandle* o
     // ---- pack the blob ------------------------------------------------------
     uint32_t off = 0;
     auto place = [&](uint32_t bytes) { uint32_t o = off; off = align16(off + bytes); return o; };
-    ds.off_nodes = place(s->n_nodes * (uint32_t)sizeof(GrtNode));
+    ds.off_nodes = place(s->n_nodes * (uint32_t)(GRT_DNODE_F4 * 16));
     ds.off_spheres = place(s->n_spheres * (uint32_t)sizeof(GrtSphere));
     ds.off_quads = place(s->n_quads * (uint32_t)sizeof(DQuadHot));
     // run-length list entries (device-internal): consecutive items of one primitive type with
@@ -496,7 +532,29 @@ extern "C" int grt_scene_upload(const GrtScene* s, int device, GrtSceneHandle* o
     if (off == 0) off = 16;
     std::vector<unsigned char> blob(off, 0);
     auto put = [&](uint32_t o, const void* p, size_t bytes) { if (bytes) memcpy(blob.data() + o, p, bytes); };
-    put(ds.off_nodes, nodes.data(), s->n_nodes * sizeof(GrtNode));
+    {   // 64-byte device nodes: the boxes of both children (dev_trace.cuh)
+        std::vector<float> dn((size_t)s->n_nodes * GRT_DNODE_F4 * 4, 0.0f);
+        const float INF = std::numeric_limits<float>::infinity();
+        auto child_box = [&](uint32_t ref, float* lo, float* hi) {
+            ref &= ~GRT_NODE_HINT_BIT;
+            if (GRT_REF_TYPE(ref) == GRT_REF_NODE) {
+                const GrtNode& c = nodes[ref & GRT_REF_MASK];
+                for (int a = 0; a < 3; a++) { lo[a] = c.bmin[a]; hi[a] = c.bmax[a]; }
+            } else {
+                for (int a = 0; a < 3; a++) { lo[a] = -INF; hi[a] = INF; }
+            }
+        };
+        for (uint32_t i = 0; i < s->n_nodes; i++) {
+            float llo[3], lhi[3], rlo[3], rhi[3];
+            child_box(nodes[i].left, llo, lhi);
+            child_box(nodes[i].right, rlo, rhi);
+            float* d = dn.data() + (size_t)i * GRT_DNODE_F4 * 4;
+            d[0] = llo[0]; d[1] = llo[1]; d[2] = llo[2]; d[3] = lhi[0]; d[4] = lhi[1]; d[5] = lhi[2];
+            d[6] = rlo[0]; d[7] = rlo[1]; d[8] = rlo[2]; d[9] = rhi[0]; d[10] = rhi[1]; d[11] = rhi[2];
+            memcpy(d + 12, &nodes[i].left, 4); memcpy(d + 13, &nodes[i].right, 4);
+        }
+        put(ds.off_nodes, dn.data(), dn.size() * sizeof(float));
+    }
     put(ds.off_spheres, s->spheres, s->n_spheres * sizeof(GrtSphere));
     {
         std::vector<DQuadHot> hot(s->n_quads);
@@ -599,11 +657,6 @@ unsigned int* grt_internal_counter(GrtSceneHandle h) { return h->d_counter; }
 
 // ---- feature-variant dispatch ------------------------------------------------
 // Each variant is a feature SUPERSET compiled as its own kernel.
-#define V_CORNELL (F_QUAD | F_BOX | F_LIST | F_ROTQUAD | F_QUAD_LIGHT)
-#define V_SMOKE (V_CORNELL | F_MEDIUM | F_ISOTROPIC)
-#define V_SPHERES (F_NODE | F_SPHERE | F_LIST | F_SPECULAR | F_TEXTURE | F_SPHERE_LIGHT | F_DEFOCUS)
-#define V_MESH (F_NODE | F_SPHERE | F_TRI | F_LIST | F_SPECULAR | F_SPHERE_LIGHT | F_TRI_LIGHT | F_TRISHADE | F_DEFOCUS)
-#define V_FULL F_ALL
 #define V_NODUP(v) ((v) & ~F_DUPIDS)
 
 template <uint32_t FEAT>
@@ -677,7 +730,7 @@ int grt_make_dev_camera(const GrtCamera* c, DevCamera* out) {
 
 template <uint32_t FEAT>
 static int launch_mega(GrtSceneDev* h, RenderParams& P, bool stats, cudaStream_t st) {
-    int blocks = h->sm_count * GRT_MEGA_MIN_BLOCKS;
+    int blocks = h->sm_count * mega_min_blocks(FEAT);
     size_t smem = h->staged ? h->ds.stage_bytes : 0;
 #define GRT_LAUNCH(STAGED_, STATS_)                                                                                           \
     do {                                                                                                                      \
@@ -688,6 +741,7 @@ static int launch_mega(GrtSceneDev* h, RenderParams& P, bool stats, cudaStream_t
     constexpr bool tiny = (FEAT & (F_NODE | F_SPHERE | F_TRI)) == 0;
     int mode = h->staged;
     if (tiny && mode == 1) { mode = 0; smem = 0; }
+    if (mega_resumable(FEAT) && smem > GRT_STAGE_MAX_BYTES_BVH) { mode = 0; smem = 0; }   // the traversal stack needs the shared memory
     if (mode == 2) { if (stats) GRT_LAUNCH(2, true); else GRT_LAUNCH(2, false); }
     else if (mode == 1) { if constexpr (!tiny) { if (stats) GRT_LAUNCH(1, true); else GRT_LAUNCH(1, false); } }
     else { if (stats) GRT_LAUNCH(0, true); else GRT_LAUNCH(0, false); }
@@ -731,6 +785,10 @@ extern "C" int grt_render_device(GrtSceneHandle h, const GrtCamera* cam, const G
     if (per_warp < 1) per_warp = 1;
     if (claim > per_warp) claim = per_warp;
     P.claim = claim;
+    {   // slice exit threshold in sixteenths; the result does not depend on it (tests/test_gpu_parity.py)
+        static const int exit16 = [] { const char* e = getenv("GRT_TRAV_EXIT16"); int b = e ? atoi(e) : -1; return b >= 0 ? b : GRT_TRAV_EXIT16; }();
+        P.trav_exit16 = exit16;
+    }
     P.rgb_sum = d_rgb_sum;
     P.counter = h->d_counter;
     P.stats = d_stats;

@@ -188,11 +188,14 @@ def test_camera_render_mirror_writes_ppm():
     assert txt.startswith(b"P3\n16 16\n255\n") and txt.count(b"\n") == 3 + 256
 
 
-@pytest.mark.parametrize("sid,w,spp", [(6, 40, 64), (7, 32, 36), (1, 40, 16), (3, 32, 16)])
+@pytest.mark.parametrize("sid,w,spp", [(6, 40, 64), (7, 32, 36), (1, 40, 16), (3, 32, 16), (8, 48, 64)])
 def test_wavefront_variant_matches_megakernel(sid, w, spp):
     """Both variants run the same arithmetic on the same Philox streams: per-pixel sums agree up to fp32
-    summation order (the wavefront variant accumulates with atomics)."""
-    s, cfg = g.builtin_scene(sid, width=w, spp=spp)
+    summation order (the wavefront variant accumulates with atomics).  On the mesh scene this also pits the
+    megakernel's resumable, warp-synchronous traversal against the plain per-lane loop of the wavefront kernels:
+    where a traversal is interrupted must not matter."""
+    kw = {"mesh_segments": 96} if sid == 8 else {}
+    s, cfg = g.builtin_scene(sid, width=w, spp=spp, **kw)
     cam = g.derive_camera(cfg)
     dev = g.DeviceScene(s)
     mega, _, _ = dev.render(cam, variant=g.GRT_VARIANT_MEGAKERNEL)

@@ -3,7 +3,8 @@ import sys
 sys.path.insert(0, ".")
 import numpy as np
 import go_raytracer_b200 as g
-import torch
+import torch, os
+VAR = int(os.environ.get("GRT_VARIANT", "0"))
 sid = int(sys.argv[1]); width = int(sys.argv[2]) if len(sys.argv) > 2 else 0; spp = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 cw = int(sys.argv[4]) if len(sys.argv) > 4 else None; cl = int(sys.argv[5]) if len(sys.argv) > 5 else None
 kw = {}
@@ -18,8 +19,8 @@ acc = torch.zeros(cam.width * cam.height * 3, dtype=torch.float32, device="cuda"
 for _ in range(2):
     acc.zero_()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(); dev.render_device(cam, acc.data_ptr()); e1.record(); torch.cuda.synchronize()
+    e0.record(); dev.render_device(cam, acc.data_ptr(), variant=VAR); e1.record(); torch.cuda.synchronize()
 paths = cam.width * cam.height * cam.spp_sqrt ** 2
-print(f"scene {sid} collapse=({cw},{cl}) {cam.width}x{cam.height}x{cam.spp_sqrt**2}: {e0.elapsed_time(e1):.1f} ms, {paths / e0.elapsed_time(e1) / 1e3:.1f} Mpaths/s")
-_, _, st = dev.render(cam, window=(0, 0, min(cam.width, 128), min(cam.height, 128)), want_stats=True)
+print(f"variant {VAR} scene {sid} collapse=({cw},{cl}) {cam.width}x{cam.height}x{cam.spp_sqrt**2}: {e0.elapsed_time(e1):.1f} ms, {paths / e0.elapsed_time(e1) / 1e3:.1f} Mpaths/s")
+_, _, st = dev.render(cam, want_stats=True)
 print({k: round(v / st["paths"], 2) for k, v in st.items() if k != "paths"}, "lanes/iter %.1f" % (st["lane_iterations"] / max(1, st["warp_iterations"])))
