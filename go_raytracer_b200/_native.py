@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GRT_CUDA_LIB") or os.path.join(_HERE, "csrc", "libgrt_cuda.so")   # env override: A/B builds
 
 GRT_OK, GRT_E_INVALID, GRT_E_NO_DEVICE, GRT_E_CUDA, GRT_E_UNSUPPORTED, GRT_E_NCCL = 0, -1, -2, -3, -4, -5
-GRT_VARIANT_MEGAKERNEL, GRT_VARIANT_WAVEFRONT = 0, 1
+GRT_VARIANT_MEGAKERNEL, GRT_VARIANT_WAVEFRONT, GRT_VARIANT_AUTO = 0, 1, 2
 GRT_OPT_STATS = 1
 GRT_NO_ID = 0xFFFFFFFF
 REF_SHIFT, REF_MASK = 28, 0x0FFFFFFF

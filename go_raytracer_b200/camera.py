@@ -105,7 +105,7 @@ class Camera:
         # backend knobs (not in the reference)
         self.Seed = 0xC0FFEE
         self.Gpus = 1
-        self.Variant = N.GRT_VARIANT_MEGAKERNEL
+        self.Variant = N.GRT_VARIANT_AUTO
 
     def PositionCamera(self, lookFrom=None, lookAt=None, vup=None):   # camera.go:65-81
         self._from = tuple(lookFrom) if lookFrom is not None else (0, 0, 0)

@@ -28,6 +28,12 @@ enum : uint32_t {
     // ~1e-7 per segment, and compiles the fallback out of its quad loop.
     F_TMIN_F64 = 1u << 16
 };
+// feature-set variants the kernels are instantiated for (a scene runs on the smallest one that covers it)
+#define V_CORNELL (F_QUAD | F_BOX | F_LIST | F_ROTQUAD | F_QUAD_LIGHT)
+#define V_SMOKE (V_CORNELL | F_MEDIUM | F_ISOTROPIC)
+#define V_SPHERES (F_NODE | F_SPHERE | F_LIST | F_SPECULAR | F_TEXTURE | F_SPHERE_LIGHT | F_DEFOCUS)
+#define V_MESH (F_NODE | F_SPHERE | F_TRI | F_LIST | F_SPECULAR | F_SPHERE_LIGHT | F_TRI_LIGHT | F_TRISHADE | F_DEFOCUS)
+#define V_FULL F_ALL
 #define GRT_NEEDS_F64(FEAT) (((FEAT) & F_SPHERE) != 0)
 
 // Device-internal quad records, repacked from GrtQuad at upload.

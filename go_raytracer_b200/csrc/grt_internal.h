@@ -35,4 +35,6 @@ const grtd::DevScene* grt_internal_dev_scene(GrtSceneHandle h);
 int grt_internal_sm_count(GrtSceneHandle h);
 int grt_internal_staged(GrtSceneHandle h);   // 0 none, 1 hot arrays, 2 whole blob
 unsigned int* grt_internal_counter(GrtSceneHandle h);
+/* the wavefront variant's path pool (grown on demand, freed with the scene) and 64 pinned bytes for its counters */
+void* grt_internal_wf_pool(GrtSceneHandle h, size_t bytes, void** pinned64);
 int grt_make_dev_camera(const GrtCamera* c, grtd::DevCamera* out);

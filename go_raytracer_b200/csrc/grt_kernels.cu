@@ -99,12 +99,6 @@ struct RenderParams {
     GrtStats* stats;
 };
 
-// feature-set variants the kernels are instantiated for (a scene runs on the smallest one that covers it)
-#define V_CORNELL (F_QUAD | F_BOX | F_LIST | F_ROTQUAD | F_QUAD_LIGHT)
-#define V_SMOKE (V_CORNELL | F_MEDIUM | F_ISOTROPIC)
-#define V_SPHERES (F_NODE | F_SPHERE | F_LIST | F_SPECULAR | F_TEXTURE | F_SPHERE_LIGHT | F_DEFOCUS)
-#define V_MESH (F_NODE | F_SPHERE | F_TRI | F_LIST | F_SPECULAR | F_SPHERE_LIGHT | F_TRI_LIGHT | F_TRISHADE | F_DEFOCUS)
-#define V_FULL F_ALL
 // The resumable, warp-synchronous traversal pays off where traversal lengths within a warp differ by orders of
 // magnitude (a large mesh next to empty space: +8 % on the 1M-triangle config); on the sphere/box BVHs of the book
 // scenes the plain per-lane loop is faster (profiles/README.md), so only the mesh variant uses it.
@@ -365,6 +359,9 @@ struct GrtSceneDev {
     void* d_texels = nullptr;
     void* d_perlins = nullptr;
     unsigned int* d_counter = nullptr;
+    void* wf_pool = nullptr;         // wavefront path pool, kept between renders (allocating 2 GB per call stalls for up to 0.4 s)
+    size_t wf_pool_bytes = 0;
+    void* wf_pinned = nullptr;
     int staged = 0;   // 0 none, 1 hot arrays, 2 whole blob
     int sm_count = 0;
 };
@@ -646,6 +643,8 @@ extern "C" int grt_scene_free(GrtSceneHandle h) {
     if (!h) return GRT_OK;
     cudaSetDevice(h->device);
     cudaFree(h->d_blob); cudaFree(h->d_tris); cudaFree(h->d_tri_shade); cudaFree(h->d_tri_v64); cudaFree(h->d_texels); cudaFree(h->d_perlins); cudaFree(h->d_counter);
+    if (h->wf_pool) cudaFree(h->wf_pool);
+    if (h->wf_pinned) cudaFreeHost(h->wf_pinned);
     delete h;
     return GRT_OK;
 }
@@ -654,6 +653,16 @@ const DevScene* grt_internal_dev_scene(GrtSceneHandle h) { return &h->ds; }
 int grt_internal_sm_count(GrtSceneHandle h) { return h->sm_count; }
 int grt_internal_staged(GrtSceneHandle h) { return h->staged; }
 unsigned int* grt_internal_counter(GrtSceneHandle h) { return h->d_counter; }
+void* grt_internal_wf_pool(GrtSceneHandle h, size_t bytes, void** pinned64) {
+    if (bytes > h->wf_pool_bytes) {
+        if (h->wf_pool) { cudaFree(h->wf_pool); h->wf_pool = nullptr; h->wf_pool_bytes = 0; }
+        if (cudaMalloc(&h->wf_pool, bytes) != cudaSuccess) { h->wf_pool = nullptr; return nullptr; }
+        h->wf_pool_bytes = bytes;
+    }
+    if (!h->wf_pinned && cudaMallocHost(&h->wf_pinned, 64) != cudaSuccess) { h->wf_pinned = nullptr; return nullptr; }
+    *pinned64 = h->wf_pinned;
+    return h->wf_pool;
+}
 
 // ---- feature-variant dispatch ------------------------------------------------
 // Each variant is a feature SUPERSET compiled as its own kernel.
@@ -757,8 +766,14 @@ extern "C" int grt_render_device(GrtSceneHandle h, const GrtCamera* cam, const G
     if (!h || !cam || !opt || !d_rgb_sum) { grt_set_error("grt_render_device: NULL argument"); return GRT_E_INVALID; }
     CUDA_TRY(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
-    if (opt->variant == GRT_VARIANT_WAVEFRONT) return grt_render_wavefront(h, cam, opt, d_rgb_sum, st, d_stats);
-    if (opt->variant != GRT_VARIANT_MEGAKERNEL) { grt_set_error("unknown GrtOptions.variant"); return GRT_E_INVALID; }
+    // AUTO: BVH scenes (book covers, meshes) go to the wavefront kernels, whose extend step copes with long, uneven
+    // traversals and many material classes; tiny list scenes (Cornell) to the megakernel.  Event counters exist only
+    // in the megakernel.
+    int variant = opt->variant;
+    if (variant == GRT_VARIANT_AUTO)
+        variant = ((h->ds.features & F_NODE) && !((opt->flags & GRT_OPT_STATS) && d_stats)) ? GRT_VARIANT_WAVEFRONT : GRT_VARIANT_MEGAKERNEL;
+    if (variant == GRT_VARIANT_WAVEFRONT) return grt_render_wavefront(h, cam, opt, d_rgb_sum, st, d_stats);
+    if (variant != GRT_VARIANT_MEGAKERNEL) { grt_set_error("unknown GrtOptions.variant"); return GRT_E_INVALID; }
     RenderParams P;
     memset(&P, 0, sizeof(P));
     int rc = grt_make_dev_camera(cam, &P.cam);

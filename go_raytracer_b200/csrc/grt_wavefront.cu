@@ -16,6 +16,8 @@
 // variants with ncu counters.
 #include <cuda_runtime.h>
 #include <string.h>
+#include <chrono>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string>
 #include "dev_shade.cuh"
@@ -26,7 +28,7 @@ using namespace grtd;
 #define WF_FREE 0xFFFFFFFFu
 enum { Q_TERMINAL = 0, Q_DIFFUSE = 1, Q_SPECULAR = 2, Q_COUNT = 3 };
 // counters[]: 0..2 queue sizes, 3 live slots after extend, 4 finished flag scratch
-enum { C_LIVE = 3, C_WORDS = 8 };
+enum { C_LIVE = 3, C_NEXT = 5, C_WORDS = 8 };   // C_NEXT: next pool slot handed out by wf_extend_dyn
 
 struct WfParams {
     DevScene scene;
@@ -47,6 +49,7 @@ struct WfParams {
     uint32_t* counters;               // C_WORDS
     unsigned long long* next_sample;
     float* rgb_sum;
+    int exit16;                       // wf_extend_dyn: a traversal slice ends when fewer than exit16/16 lanes have work
 };
 
 template <int STAGED>
@@ -130,6 +133,96 @@ __global__ void __launch_bounds__(256) wf_extend(const __grid_constant__ WfParam
     if (live && lane == 0) atomicAdd(P.counters + C_LIVE, (uint32_t)__popc(live));
 }
 
+
+// ---- extend for BVH scenes: persistent warps, dynamic ray fetch ----------------------------------
+// Traversal lengths on a large BVH differ by orders of magnitude (a ray that misses the mesh is done after one
+// node, a grazing one visits hundreds), so one-thread-per-slot leaves most lanes of a warp idle behind its
+// longest ray.  Here the warps are persistent: all 32 lanes run warp-synchronous traversal slices
+// (trav_run<VOTE>, shared-memory stacks), and whenever a slice ends the lanes whose ray is finished write
+// their hit, enqueue the slot and fetch the next live slot from a global counter.  Slots are independent, so
+// unlike the megakernel nothing ties a lane to a pixel.
+#define WF_DYN_THREADS 128
+#ifndef WF_DYN_MIN_BLOCKS
+#define WF_DYN_MIN_BLOCKS 6
+#endif
+template <uint32_t FEAT, int STAGED>
+__global__ void __launch_bounds__(WF_DYN_THREADS, WF_DYN_MIN_BLOCKS) wf_extend_dyn(const __grid_constant__ WfParams P) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    SceneView sv = wf_view<STAGED>(P, smem);
+    __shared__ uint32_t trav_smem[GRT_TRAV_SMEM][WF_DYN_THREADS];
+    TravState<false, WF_DYN_THREADS> ts;
+    ts.ext = &trav_smem[0][threadIdx.x];
+    ts.sp = 0;
+    const unsigned FULL = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const float INF = __int_as_float(0x7f800000);
+    bool have = false, exhausted = false;
+    uint32_t slot = 0, self_ref = 0xFFFFFFFFu, med_count = 0;
+    uint4 s3 = make_uint4(0, 0, 0, GRT_NO_ID);
+    RayD ray;
+    ray_setup<FEAT>(ray, mk3(0, 0, 0), mk3(0, 0, 1), 0.0f);
+    for (;;) {
+        const unsigned need = __ballot_sync(FULL, !have);
+        if (need && !exhausted) {
+            const int leader = __ffs(need) - 1;
+            uint32_t base = 0;
+            if ((int)lane == leader) base = atomicAdd(P.counters + C_NEXT, (uint32_t)__popc(need));
+            base = __shfl_sync(FULL, base, leader);
+            if (base >= P.P) exhausted = true;
+            if (!have) {
+                const uint32_t sl = base + (uint32_t)__popc(need & lt_mask);
+                if (sl < P.P) {
+                    const uint4 v = P.S3[sl];
+                    if (v.z != WF_FREE) {
+                        slot = sl; s3 = v;
+                        const float4 s0 = P.S0[sl], s1 = P.S1[sl];
+                        ray_setup<FEAT>(ray, mk3(s0.x, s0.y, s0.z), mk3(s1.x, s1.y, s1.z), s0.w);
+                        self_ref = __float_as_uint(s1.w);
+                        trav_begin(ts, P.scene.root, INF);
+                        med_count = 0;
+                        have = true;
+                    }
+                }
+            }
+        }
+        if (!__any_sync(FULL, have)) { if (exhausted) break; else continue; }
+        MediumRngCtx mr;
+        mr.pixel = s3.x; mr.sample = s3.y; mr.bounce = s3.z & 255u; mr.k0 = P.k0; mr.k1 = P.k1; mr.count = med_count;
+        const bool fin = trav_run<FEAT, false, false, true>(sv, ts, ray, 0.001f, s3.w, self_ref, &mr, nullptr, FULL, P.exit16);
+        med_count = mr.count;
+        int q = -1;
+        if (have && fin) {
+            HitInfo h;
+            const bool hit = trav_end<FEAT>(sv, ts, ray, h);
+            if (!hit) { h.t = INF; h.ref = GRT_MAKE_REF(GRT_REF_NONE, 0); h.u = h.v = 0; q = Q_TERMINAL; }
+            else {
+                uint32_t type = GRT_REF_TYPE(h.ref), idx = h.ref & GRT_REF_MASK, mat;
+                if ((FEAT & F_QUAD) && type == GRT_REF_QUAD) mat = sv.quads_cold()[idx].mat;
+                else if ((FEAT & F_SPHERE) && type == GRT_REF_SPHERE) mat = sv.spheres()[idx].mat;
+                else if ((FEAT & F_TRI) && type == GRT_REF_TRI) mat = P.scene.tris[idx].mat;
+                else mat = sv.media()[idx].mat;
+                uint32_t mt = sv.materials()[mat].type;
+                q = (mt == GRT_MAT_DIFFUSE_LIGHT) ? Q_TERMINAL : ((mt == GRT_MAT_METAL || mt == GRT_MAT_DIELECTRIC) ? Q_SPECULAR : Q_DIFFUSE);
+            }
+            P.H[slot] = make_float4(h.t, __uint_as_float(h.ref), h.u, h.v);
+            have = false;
+        }
+#pragma unroll
+        for (int k = 0; k < Q_COUNT; k++) {
+            unsigned m = __ballot_sync(FULL, q == k);
+            if (!m) continue;
+            uint32_t base = 0;
+            int leader = __ffs(m) - 1;
+            if ((int)lane == leader) base = atomicAdd(P.counters + k, (uint32_t)__popc(m));
+            base = __shfl_sync(FULL, base, leader);
+            if (q == k) P.queues[(size_t)k * P.P + base + __popc(m & lt_mask)] = slot;
+        }
+        unsigned live = __ballot_sync(FULL, q >= 0);
+        if (live && lane == 0) atomicAdd(P.counters + C_LIVE, (uint32_t)__popc(live));
+    }
+}
+
 // ---- shade ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void wf_finish_path(const WfParams& P, uint32_t slot, uint32_t pixel_index, f3 L) {
     if (L.x != 0.0f || L.y != 0.0f || L.z != 0.0f) {   // NaN != 0 is true: a NaN sample is accumulated (color.go:28-36)
@@ -211,13 +304,17 @@ __global__ void wf_init_slots(uint4* S3, uint32_t P) {
         if (e_ != cudaSuccess) { grt_set_error(std::string("wavefront: ") + #call + ": " + cudaGetErrorString(e_)); rc = GRT_E_CUDA; goto done; } \
     } while (0)
 
-#define V_CORNELL (F_QUAD | F_BOX | F_LIST | F_ROTQUAD | F_QUAD_LIGHT)
-#define V_SMOKE (V_CORNELL | F_MEDIUM | F_ISOTROPIC)
-
 template <uint32_t FEAT>
 static int wf_run(GrtSceneHandle h, WfParams& P, cudaStream_t st, uint32_t* h_counters) {
     int rc = GRT_OK;
-    const bool staged = grt_internal_staged(h) == 2;   // whole-blob staging or none
+    // Triangle meshes: persistent extend with dynamic ray fetch (166 -> 271 Mpaths/s on the 1M-triangle config).  The
+    // sphere / box BVHs of the book scenes have short, even traversals and expensive leaves; the plain
+    // one-thread-per-slot extend is faster there (311 vs 252 and 720 vs 633 Mpaths/s; profiles/README.md).
+    constexpr bool can_dyn = (FEAT & F_NODE) != 0 && (FEAT & F_TRI) != 0;
+    bool dyn = can_dyn && P.scene.n_tris >= 1024u;
+    if (const char* e = getenv("GRT_WF_DYN")) dyn = can_dyn && (atoi(e) == 2 || (dyn && atoi(e) != 0));   // 0: never, 2: whenever compiled in
+    const bool staged = grt_internal_staged(h) == 2 && !dyn;   // whole-blob staging or none
+    const unsigned dyn_blocks = (unsigned)grt_internal_sm_count(h) * WF_DYN_MIN_BLOCKS;
     const size_t smem = staged ? P.scene.stage_bytes : 0;
     const unsigned blocks = (P.P + 255) / 256;
     const bool has_spec = (P.scene.features & F_SPECULAR) != 0;
@@ -234,7 +331,15 @@ static int wf_run(GrtSceneHandle h, WfParams& P, cudaStream_t st, uint32_t* h_co
     for (uint64_t iter = 0;; iter++) {
         CU(cudaMemsetAsync(P.counters, 0, C_WORDS * 4, st));
         wf_generate<FEAT><<<blocks, 256, 0, st>>>(P);
-        if (staged) {
+        if (dyn) {
+            if constexpr (can_dyn) {
+                // the scene is read from global memory (L1/L2): the shared memory holds the traversal stacks
+                wf_extend_dyn<FEAT, 0><<<dyn_blocks, WF_DYN_THREADS, 0, st>>>(P);
+                wf_shade<FEAT, 0, Q_TERMINAL><<<blocks, 256, 0, st>>>(P);
+                wf_shade<FEAT, 0, Q_DIFFUSE><<<blocks, 256, 0, st>>>(P);
+                if (has_spec) wf_shade<FEAT, 0, Q_SPECULAR><<<blocks, 256, 0, st>>>(P);
+            }
+        } else if (staged) {
             wf_extend<FEAT, 2><<<blocks, 256, smem, st>>>(P);
             wf_shade<FEAT, 2, Q_TERMINAL><<<blocks, 256, smem, st>>>(P);
             wf_shade<FEAT, 2, Q_DIFFUSE><<<blocks, 256, smem, st>>>(P);
@@ -256,6 +361,7 @@ static int wf_run(GrtSceneHandle h, WfParams& P, cudaStream_t st, uint32_t* h_co
     CU(cudaGetLastError());
 done:
     grt_count_launch(launches);
+    if (getenv("GRT_WF_TRACE")) fprintf(stderr, "[wavefront] %llu launches, dyn=%d, pool=%u slots\n", (unsigned long long)launches, (int)dyn, P.P);
     return rc;
 }
 
@@ -283,12 +389,20 @@ int grt_render_wavefront(GrtSceneHandle h, const GrtCamera* cam, const GrtOption
     unsigned long long want = P.total < pool_slots ? P.total : pool_slots;
     P.P = (uint32_t)((want + 255) / 256 * 256);
     P.rgb_sum = d_rgb_sum;
+    P.exit16 = 12;
+    if (const char* e = getenv("GRT_WF_EXIT16")) { int v = atoi(e); if (v >= 0 && v <= 16) P.exit16 = v; }
     void* pool = nullptr;
     uint32_t* h_counters = nullptr;
+    const bool trace = getenv("GRT_WF_TRACE") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_a = now(), t_b = 0, t_c = 0;
     {
         size_t n = P.P;
         size_t bytes = n * 16 * 5 + n * 16 * (size_t)(cam->max_depth + 1) + n * 4 * Q_COUNT + C_WORDS * 4 + 64;
-        CU(cudaMalloc(&pool, bytes));
+        void* pinned = nullptr;
+        pool = grt_internal_wf_pool(h, bytes, &pinned);
+        if (!pool) { grt_set_error("wavefront: cannot allocate the path pool"); rc = GRT_E_CUDA; goto done; }
+        h_counters = (uint32_t*)pinned;
         unsigned char* p = (unsigned char*)pool;
         P.S0 = (float4*)p; p += n * 16; P.S1 = (float4*)p; p += n * 16; P.S2 = (float4*)p; p += n * 16;
         P.S3 = (uint4*)p; p += n * 16; P.H = (float4*)p; p += n * 16;
@@ -297,17 +411,19 @@ int grt_render_wavefront(GrtSceneHandle h, const GrtCamera* cam, const GrtOption
         P.counters = (uint32_t*)p; p += C_WORDS * 4;
         p = (unsigned char*)(((uintptr_t)p + 15) & ~(uintptr_t)15);
         P.next_sample = (unsigned long long*)p;
-        CU(cudaMallocHost((void**)&h_counters, C_WORDS * 4));
     }
+    t_b = now();
     {
         uint32_t f = (P.scene.features & ~F_DUPIDS) | (cam->defocus_angle > 0 ? F_DEFOCUS : 0u);
         bool dup = (P.scene.features & F_DUPIDS) != 0;
         if (!dup && (f & ~V_CORNELL) == 0) rc = wf_run<V_CORNELL>(h, P, st, h_counters);
         else if (!dup && (f & ~V_SMOKE) == 0) rc = wf_run<V_SMOKE>(h, P, st, h_counters);
+        else if (!dup && (f & ~V_SPHERES) == 0) rc = wf_run<V_SPHERES>(h, P, st, h_counters);
+        else if (!dup && (f & ~V_MESH) == 0) rc = wf_run<V_MESH>(h, P, st, h_counters);
         else rc = wf_run<F_ALL>(h, P, st, h_counters);
     }
 done:
-    if (pool) { cudaStreamSynchronize(st); cudaFree(pool); }
-    if (h_counters) cudaFreeHost(h_counters);
+    if (pool) { cudaStreamSynchronize(st); t_c = now(); }   // the pool stays with the scene handle
+    if (trace) fprintf(stderr, "[wavefront] alloc %.1f ms, render %.1f ms, free %.1f ms\n", t_b - t_a, t_c - t_b, now() - t_c);
     return rc;
 }

@@ -10,7 +10,7 @@
 
 int main(int argc, char** argv) {
     std::string outFile = "image.ppm";
-    int scene = -1, gpus = 1, variant = GRT_VARIANT_MEGAKERNEL, width = 0, spp = 0;
+    int scene = -1, gpus = 1, variant = GRT_VARIANT_AUTO, width = 0, spp = 0;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         auto val = [&](const char* name) -> const char* {
@@ -26,7 +26,7 @@ int main(int argc, char** argv) {
         else if ((v = val("o")) || (v = val("outfile"))) outFile = v;   // main.go:419 defines -o; the README says -outfile
         else if ((v = val("cpuprofile"))) (void)v;
         else if ((v = val("gpus"))) gpus = atoi(v);
-        else if ((v = val("variant"))) variant = (strcmp(v, "wavefront") == 0) ? GRT_VARIANT_WAVEFRONT : GRT_VARIANT_MEGAKERNEL;
+        else if ((v = val("variant"))) variant = (strcmp(v, "wavefront") == 0) ? GRT_VARIANT_WAVEFRONT : (strcmp(v, "mega") == 0 || strcmp(v, "megakernel") == 0) ? GRT_VARIANT_MEGAKERNEL : GRT_VARIANT_AUTO;
         else if ((v = val("width"))) width = atoi(v);
         else if ((v = val("spp"))) spp = atoi(v);
         else { fprintf(stderr, "flag provided but not defined: %s\nUsage: -S int -N int -o string -cpuprofile string [-gpus int] [-variant mega|wavefront]\n", a.c_str()); return 2; }

@@ -242,6 +242,7 @@ typedef struct GrtCamera {
 
 #define GRT_VARIANT_MEGAKERNEL 0
 #define GRT_VARIANT_WAVEFRONT  1
+#define GRT_VARIANT_AUTO       2   /* wavefront for scenes with a BVH (measured faster there), megakernel otherwise */
 typedef struct GrtOptions {
     uint64_t seed;                   /* Philox key                          */
     int32_t  variant;                /* GRT_VARIANT_*                       */

@@ -188,7 +188,7 @@ def test_camera_render_mirror_writes_ppm():
     assert txt.startswith(b"P3\n16 16\n255\n") and txt.count(b"\n") == 3 + 256
 
 
-@pytest.mark.parametrize("sid,w,spp", [(6, 40, 64), (7, 32, 36), (1, 40, 16), (3, 32, 16), (8, 48, 64)])
+@pytest.mark.parametrize("sid,w,spp", [(6, 40, 64), (7, 32, 36), (1, 40, 16), (3, 32, 16), (8, 48, 64), (2, 40, 16), (5, 40, 16)])
 def test_wavefront_variant_matches_megakernel(sid, w, spp):
     """Both variants run the same arithmetic on the same Philox streams: per-pixel sums agree up to fp32
     summation order (the wavefront variant accumulates with atomics).  On the mesh scene this also pits the
@@ -277,3 +277,24 @@ def test_flatten_options_do_not_change_the_image():
     assert close.mean() > 0.995          # identical paths except where an fp32 tie falls the other way
     os_, _, _, _ = O.OracleWorld(sc).render(cam.config(), use_exclusion=True)
     assert np.isclose(a, os_, rtol=1e-3, atol=1e-3).mean() > 0.99
+
+
+def test_auto_variant_picks_by_scene_and_keeps_the_image():
+    """GRT_VARIANT_AUTO: megakernel for list-only scenes (bit-identical to asking for it), wavefront kernels for BVH
+    scenes (same per-pixel sums up to fp32 summation order)."""
+    s, cfg = g.builtin_scene(6, width=32, spp=16)
+    cam = g.derive_camera(cfg)
+    dev = g.DeviceScene(s)
+    a, _, _ = dev.render(cam, variant=g.GRT_VARIANT_AUTO)
+    m, _, _ = dev.render(cam, variant=g.GRT_VARIANT_MEGAKERNEL)
+    assert np.array_equal(a, m, equal_nan=True)
+    s, cfg = g.builtin_scene(1, width=40, spp=16)
+    cam = g.derive_camera(cfg)
+    dev = g.DeviceScene(s)
+    a, _, _ = dev.render(cam, variant=g.GRT_VARIANT_AUTO)
+    m, _, _ = dev.render(cam, variant=g.GRT_VARIANT_MEGAKERNEL)
+    fin = np.isfinite(a) & np.isfinite(m)
+    assert fin.mean() > 0.999 and np.allclose(a[fin], m[fin], rtol=1e-4, atol=1e-4)
+    # event counters exist only in the megakernel: asking for them keeps AUTO there
+    _, _, st = dev.render(cam, variant=g.GRT_VARIANT_AUTO, want_stats=True)
+    assert st["paths"] == cam.width * cam.height * cam.spp_sqrt ** 2

@@ -16,10 +16,12 @@ s, cfg = g.builtin_scene(sid, width=width, spp=spp, **kw)
 dev = g.DeviceScene(s, 0, cw, cl)
 cam = g.derive_camera(cfg)
 acc = torch.zeros(cam.width * cam.height * 3, dtype=torch.float32, device="cuda")
-for _ in range(2):
-    acc.zero_()
+import time
+for _ in range(int(os.environ.get("REPS", "2"))):
+    acc.zero_(); torch.cuda.synchronize(); t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); dev.render_device(cam, acc.data_ptr(), variant=VAR); e1.record(); torch.cuda.synchronize()
+    if os.environ.get("REPS"): print("  rep: %.1f ms (events)  %.1f ms (wall)" % (e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0)))
 paths = cam.width * cam.height * cam.spp_sqrt ** 2
 print(f"variant {VAR} scene {sid} collapse=({cw},{cl}) {cam.width}x{cam.height}x{cam.spp_sqrt**2}: {e0.elapsed_time(e1):.1f} ms, {paths / e0.elapsed_time(e1) / 1e3:.1f} Mpaths/s")
 _, _, st = dev.render(cam, want_stats=True)
