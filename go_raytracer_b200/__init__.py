@@ -6,10 +6,10 @@ Go API used by tests and bench: `Scene` (package hittable's constructors),
 `Camera` (camera.Camera) and `DeviceScene` (upload / trace_batch / render).
 """
 from ._native import (GrtError, GrtCameraConfig, GrtCamera, GrtOptions, GrtStats, GrtScene, RAY_DTYPE, HIT_DTYPE,
-                      GRT_VARIANT_MEGAKERNEL, GRT_VARIANT_WAVEFRONT, GRT_VARIANT_AUTO, GRT_NO_ID, lib, LIB_PATH)
+                      GRT_VARIANT_MEGAKERNEL, GRT_VARIANT_WAVEFRONT, GRT_VARIANT_AUTO, GRT_NO_ID, lib, LIB_PATH, bvh_order)
 from .scene import Scene, builtin_scene, SCENE_NAMES, PERLIN, MARBLE, TURBULENT
 from .camera import Camera, DeviceScene, derive_camera, write_ppm
 
 __all__ = ["GrtError", "GrtCameraConfig", "GrtCamera", "GrtOptions", "GrtStats", "GrtScene", "RAY_DTYPE", "HIT_DTYPE",
-           "GRT_VARIANT_MEGAKERNEL", "GRT_VARIANT_WAVEFRONT", "GRT_VARIANT_AUTO", "GRT_NO_ID", "lib", "LIB_PATH", "Scene", "builtin_scene",
+           "GRT_VARIANT_MEGAKERNEL", "GRT_VARIANT_WAVEFRONT", "GRT_VARIANT_AUTO", "GRT_NO_ID", "lib", "LIB_PATH", "bvh_order", "Scene", "builtin_scene",
            "SCENE_NAMES", "PERLIN", "MARBLE", "TURBULENT", "Camera", "DeviceScene", "derive_camera", "write_ppm"]

@@ -113,6 +113,15 @@ assert MATERIAL_DTYPE.itemsize == 32 and TEXTURE_DTYPE.itemsize == 32 and BOX_DT
 _lib = None
 
 
+def bvh_order(boxes, device=0):
+    """grt_bvh_order: the object order BuildBVH (bvh.go:21-61) ends with, computed on the GPU.
+    boxes: (n, 6) float64 {lo.xyz, hi.xyz} in list order; returns order[p] = list index at position p."""
+    b = np.ascontiguousarray(boxes, dtype=np.float64).reshape(-1, 6)
+    out = np.empty(b.shape[0], dtype=np.uint32)
+    check(lib().grt_bvh_order(b.ctypes.data, b.shape[0], int(device), out.ctypes.data))
+    return out
+
+
 def lib():
     """Load libgrt_cuda.so (fails loudly when it has not been built)."""
     global _lib
@@ -126,7 +135,7 @@ def lib():
     P = C.POINTER
     sig = {
         "grt_abi_version": (i32, []), "grt_device_count": (i32, []), "grt_last_error": (C.c_char_p, []),
-        "grt_launch_count": (u64, []),
+        "grt_launch_count": (u64, []), "grt_bvh_order": (i32, [vp, C.c_uint32, i32, vp]),
         "grt_scene_upload": (i32, [P(GrtScene), i32, P(vp)]), "grt_scene_free": (i32, [vp]),
         "grt_trace_batch": (i32, [vp, vp, u64, vp]), "grt_trace_batch_device": (i32, [vp, vp, u64, vp, vp]),
         "grt_render": (i32, [vp, P(GrtCamera), P(GrtOptions), vp, vp, P(GrtStats)]),
@@ -166,7 +175,7 @@ EXPORTED_SYMBOLS = [
     # include/grt.h
     "grt_abi_version", "grt_device_count", "grt_last_error", "grt_scene_upload", "grt_scene_free", "grt_trace_batch",
     "grt_trace_batch_device", "grt_render", "grt_render_device", "grt_tonemap_device", "grt_render_multi",
-    "grt_launch_count",
+    "grt_launch_count", "grt_bvh_order",
     # include/grt_host.h
     "grt_host_last_error", "grt_host_scene_new", "grt_host_scene_free", "grt_host_solid_color", "grt_host_checkerboard",
     "grt_host_image", "grt_host_image_texture", "grt_host_noise_texture", "grt_host_lambertian", "grt_host_metal",

@@ -15,6 +15,10 @@
 //     precomputed A = v×w, B = w×u used by the device interior test.
 // This is the Go-side `hittable.Flatten` of INTEGRATION.md written in C++.
 #pragma once
+#include <cstdlib>
+#include <cstdio>
+#include <chrono>
+#include <functional>
 #include "scene_ir.hpp"
 #include "../../include/grt.h"
 #include <algorithm>
@@ -126,6 +130,11 @@ struct FlattenOptions {
     int collapse_leaf = 4;     // inside larger trees, subtrees with at most this many leaves become lists
     bool box_prims = true;     // NewBox results are found with one slab test (GrtBox) instead of six quad tests
     bool order_hints = true;   // nodes carry the split axis so a ray may visit the nearer child first
+    // BuildBVH's object order computed elsewhere (the GPU, grt_bvh_order) for lists of at least gpu_order_min
+    // objects: boxes = n x {lo.xyz, hi.xyz}, order[p] = list index of the object at position p.  Returns false
+    // to make the flattener sort on the host.
+    std::function<bool(const double* boxes, uint32_t n, uint32_t* order)> gpu_order;
+    size_t gpu_order_min = 32768;
 };
 
 class Flattener {
@@ -140,7 +149,9 @@ class Flattener {
             refBoxCache.assign(S.hittables.size(), RefBox());
             refBoxDone.assign(S.hittables.size(), 0);
             emitMaterials();
+            const double t_emit = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
             Emitted e = emit(S.world, Xform(), false);
+            if (getenv("GRT_FLATTEN_TRACE")) fprintf(stderr, "[flatten] emit (incl. BuildBVH) %.3f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count() - t_emit);
             F->root = e.ref;
             F->max_depth_hint = (uint32_t)std::max(e.need + 1, mediumNeed + 1);
             emitLights();
@@ -260,7 +271,7 @@ class Flattener {
         return refBoxCache[hid];
     }
 
-    int buildRange(Topology& T, std::vector<int>& objs, size_t start, size_t end) {
+    int buildRange(Topology& T, std::vector<int>& objs, size_t start, size_t end, bool presorted = false) {
         RefBox bb = emptyBox();
         for (size_t i = start; i < end; i++) bb = fromBoxes(bb, refBox(objs[i]));
         int axis = longestAxis(bb);
@@ -272,14 +283,14 @@ class Flattener {
         else {
             // boxCompare (bvh.go:25-32).  Go's sort.Slice is not stable; equal keys are
             // documented as unordered, we keep list order for them.
-            std::stable_sort(objs.begin() + start, objs.begin() + end, [&](int a, int b) {
+            if (!presorted) std::stable_sort(objs.begin() + start, objs.begin() + end, [&](int a, int b) {
                 const RefBox &A = refBoxCache[a], &B = refBoxCache[b];
                 if (A.lo[axis] != B.lo[axis]) return A.lo[axis] < B.lo[axis];
                 return A.hi[axis] < B.hi[axis];
             });
             size_t mid = start + span / 2;
-            n.left = buildRange(T, objs, start, mid);
-            n.right = buildRange(T, objs, mid, end);
+            n.left = buildRange(T, objs, start, mid, presorted);
+            n.right = buildRange(T, objs, mid, end, presorted);
             n.leftIsNode = n.rightIsNode = true;
             n.axis = axis;
             n.leaves = T.nodes[n.left].leaves + T.nodes[n.right].leaves;
@@ -293,8 +304,31 @@ class Flattener {
         Topology T;
         std::vector<int> objs = S.lists[listPayload];
         if (objs.empty()) throw std::runtime_error("BuildBVH of an empty list (the reference would index out of range)");
+        auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        const bool trace = getenv("GRT_FLATTEN_TRACE") != nullptr && objs.size() > 1000;
+        double t0 = now();
         for (int o : objs) (void)refBox(o);
-        T.root = buildRange(T, objs, 0, objs.size());
+        double t1 = now();
+        bool presorted = false;
+        if (opt.gpu_order && objs.size() >= opt.gpu_order_min) {
+            // the final order of all recursive sorts, computed level by level on the device (grt_bvh.cu)
+            std::vector<double> boxes(objs.size() * 6);
+            for (size_t i = 0; i < objs.size(); i++) {
+                const RefBox& b = refBoxCache[objs[i]];
+                for (int a = 0; a < 3; a++) { boxes[6 * i + a] = b.lo[a]; boxes[6 * i + 3 + a] = b.hi[a]; }
+            }
+            std::vector<uint32_t> order(objs.size());
+            if (opt.gpu_order(boxes.data(), (uint32_t)objs.size(), order.data())) {
+                std::vector<int> sorted(objs.size());
+                for (size_t p = 0; p < objs.size(); p++) sorted[p] = objs[order[p]];
+                objs.swap(sorted);
+                presorted = true;
+            }
+        }
+        double t2 = now();
+        T.root = buildRange(T, objs, 0, objs.size(), presorted);
+        if (trace) fprintf(stderr, "[flatten] BuildBVH of %zu objects: boxes %.3f s, %s order %.3f s, tree %.3f s\n", objs.size(), t1 - t0,
+                           presorted ? "GPU" : "no separate", t2 - t1, now() - t2);
         return topoCache.emplace(listPayload, std::move(T)).first->second;
     }
 

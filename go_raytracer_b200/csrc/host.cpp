@@ -2,6 +2,8 @@
 #include "../../include/grt_host.h"
 #include "scene_ir.hpp"
 #include "scenes.hpp"
+#include <stdlib.h>
+#include <string.h>
 #include "flatten.hpp"
 #include "obj_loader.hpp"
 #include <cstdio>
@@ -145,6 +147,15 @@ int grt_host_flatten_opts(GrtHostScene* s, int collapse_whole, int collapse_leaf
     grt::flat::FlattenOptions fo;
     fo.collapse_whole = collapse_whole < 0 ? 0 : collapse_whole; fo.collapse_leaf = collapse_leaf;
     if (collapse_whole == 0 && collapse_leaf == 0) { fo.box_prims = false; fo.order_hints = false; }   // (0, 0): the reference's tree, node for node
+    {   // BuildBVH's sorts run on the GPU for large lists when a device is present (GRT_BVH_BUILD=cpu|gpu overrides:
+        // "cpu" never, "gpu" for every list of three or more objects)
+        const char* e = getenv("GRT_BVH_BUILD");
+        const bool never = e && strcmp(e, "cpu") == 0;
+        if (!never && grt_device_count() > 0) {
+            fo.gpu_order = [](const double* boxes, uint32_t n, uint32_t* order) { return grt_bvh_order(boxes, n, 0, order) == 0; };
+            if (e && strcmp(e, "gpu") == 0) fo.gpu_order_min = 3;
+        }
+    }
     grt::flat::Flattener f(s->ir, fo);
     if (!f.run(*s->flat)) { s->flat.reset(); return fail(f.error); }
     *out = s->flat->view();

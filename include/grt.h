@@ -330,6 +330,12 @@ int grt_render_multi(const GrtScene* scene, const GrtCamera* cam, const GrtOptio
                      const int* devices, int n_devices,
                      float* rgb_sum, uint8_t* rgb8, double* kernel_ms);
 
+/* BuildBVH's object order on the GPU: replaces the per-node sort.Slice of bvhHelper (bvh.go:35-61, boxCompare
+ * bvh.go:25-32, LongestAxis aabb.go:73-87) for large lists.  boxes = n x {lo.x, lo.y, lo.z, hi.x, hi.y, hi.z}, the
+ * objects' BBox() in list order; order_out[p] = list index of the object that stands at position p after all
+ * recursive sorts (ties keep list order).  The tree's shape follows from n alone (median splits). */
+int grt_bvh_order(const double* boxes, uint32_t n, int device, uint32_t* order_out);
+
 /* Kernel launch count since library load (bench.py's gpu_launches claim). */
 uint64_t grt_launch_count(void);
 

@@ -59,3 +59,34 @@ def compare_hits(gpu, orc, audit=True, t_rel=1e-5):
         "t_max_rel_unflagged": float(rel[both & ~flagged].max()) if (both & ~flagged).any() else 0.0,
         "t_bad": int(bad_t.sum()), "bad_id_idx": np.nonzero(bad_id)[0][:10], "bad_t_idx": np.nonzero(bad_t)[0][:10],
     }
+
+
+def ref_bvh_order(boxes):
+    """CPU checker for grt_bvh_order: the object order bvhHelper (bvh.go:35-61) ends with — every span of >= 3
+    objects sorted (stably) by boxCompare (bvh.go:25-32) along LongestAxis (aabb.go:73-87) of the span's padded
+    union box (aabb.go:54-59,118-129), split at the median, recursively."""
+    import numpy as np
+    b = np.asarray(boxes, dtype=np.float64).reshape(-1, 6)
+    order = np.arange(b.shape[0])
+    stack = [(0, b.shape[0])]
+    while stack:
+        s, e = stack.pop()
+        if e - s < 3:
+            continue
+        idx = order[s:e]
+        lo, hi = b[idx, :3].min(axis=0), b[idx, 3:].max(axis=0)
+        size = []
+        for a in range(3):
+            l, h = lo[a], hi[a]
+            if h - l < 0.0001:
+                l, h = l - 0.0001 / 2, h + 0.0001 / 2
+            size.append(h - l)
+        if size[0] > size[1]:
+            axis = 0 if size[0] > size[2] else 2
+        else:
+            axis = 1 if size[1] > size[2] else 2
+        k = np.lexsort((b[idx, 3 + axis], b[idx, axis]))    # stable; primary key = box min, then box max
+        order[s:e] = idx[k]
+        mid = s + (e - s) // 2
+        stack.append((s, mid)); stack.append((mid, e))
+    return order
