@@ -271,30 +271,41 @@ class Flattener {
         return refBoxCache[hid];
     }
 
-    int buildRange(Topology& T, std::vector<int>& objs, size_t start, size_t end, bool presorted = false) {
-        RefBox bb = emptyBox();
-        for (size_t i = start; i < end; i++) bb = fromBoxes(bb, refBox(objs[i]));
-        int axis = longestAxis(bb);
+    // `presorted`: objs already stands in BuildBVH's final order (grt_bvh_order), so nothing is sorted here and a span's
+    // box — needed only for its longest axis — is the union of its halves' boxes instead of a pass over all its objects.
+    int buildRange(Topology& T, std::vector<int>& objs, size_t start, size_t end, bool presorted = false, RefBox* box_out = nullptr) {
         size_t span = end - start;
         BuildNode n;
         n.axis = -1;   // only a sorted split (span >= 3) orders its children along `axis`
+        RefBox bb = emptyBox();
+        if (!presorted || span <= 2) for (size_t i = start; i < end; i++) bb = fromBoxes(bb, refBox(objs[i]));
         if (span == 1) { n.left = n.right = objs[start]; n.leftIsNode = n.rightIsNode = false; n.leaves = leafCount(objs[start]); }
         else if (span == 2) { n.left = objs[start]; n.right = objs[start + 1]; n.leftIsNode = n.rightIsNode = false; n.leaves = leafCount(objs[start]) + leafCount(objs[start + 1]); }
         else {
-            // boxCompare (bvh.go:25-32).  Go's sort.Slice is not stable; equal keys are
-            // documented as unordered, we keep list order for them.
-            if (!presorted) std::stable_sort(objs.begin() + start, objs.begin() + end, [&](int a, int b) {
-                const RefBox &A = refBoxCache[a], &B = refBoxCache[b];
-                if (A.lo[axis] != B.lo[axis]) return A.lo[axis] < B.lo[axis];
-                return A.hi[axis] < B.hi[axis];
-            });
             size_t mid = start + span / 2;
-            n.left = buildRange(T, objs, start, mid, presorted);
-            n.right = buildRange(T, objs, mid, end, presorted);
+            if (!presorted) {
+                int axis = longestAxis(bb);
+                // boxCompare (bvh.go:25-32).  Go's sort.Slice is not stable; equal keys are
+                // documented as unordered, we keep list order for them.
+                std::stable_sort(objs.begin() + start, objs.begin() + end, [&](int a, int b) {
+                    const RefBox &A = refBoxCache[a], &B = refBoxCache[b];
+                    if (A.lo[axis] != B.lo[axis]) return A.lo[axis] < B.lo[axis];
+                    return A.hi[axis] < B.hi[axis];
+                });
+                n.left = buildRange(T, objs, start, mid);
+                n.right = buildRange(T, objs, mid, end);
+                n.axis = axis;
+            } else {
+                RefBox lb, rb;
+                n.left = buildRange(T, objs, start, mid, true, &lb);
+                n.right = buildRange(T, objs, mid, end, true, &rb);
+                bb = fromBoxes(lb, rb);
+                n.axis = longestAxis(bb);
+            }
             n.leftIsNode = n.rightIsNode = true;
-            n.axis = axis;
             n.leaves = T.nodes[n.left].leaves + T.nodes[n.right].leaves;
         }
+        if (box_out) *box_out = bb;
         T.nodes.push_back(n);
         return (int)T.nodes.size() - 1;
     }
