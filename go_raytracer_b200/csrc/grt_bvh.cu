@@ -177,7 +177,7 @@ extern "C" int grt_bvh_order(const double* boxes, uint32_t n, int device, uint32
     int prev_dev = 0;
     cudaGetDevice(&prev_dev);
     double* d_boxes = nullptr;
-    uint32_t *d_order = nullptr, *d_order2 = nullptr, *d_span_of = nullptr, *d_axis = nullptr;
+    uint32_t *d_order = nullptr, *d_span_of = nullptr, *d_axis = nullptr;
     uint2* d_spans = nullptr;
     unsigned long long* d_sbox = nullptr;
     SortKey* d_keys = nullptr;
@@ -187,15 +187,15 @@ extern "C" int grt_bvh_order(const double* boxes, uint32_t n, int device, uint32
     for (auto& l : levels) max_spans = l.size() > max_spans ? l.size() : max_spans;
     const unsigned T = 256, B = (n + T - 1) / T;
     BVH_TRY(cudaSetDevice(device));
-    BVH_TRY(cudaMalloc(&d_boxes, (size_t)n * 48));
-    BVH_TRY(cudaMalloc(&d_order, (size_t)n * 4));
-    BVH_TRY(cudaMalloc(&d_span_of, (size_t)n * 4));
-    BVH_TRY(cudaMalloc(&d_keys, (size_t)n * sizeof(SortKey)));
-    BVH_TRY(cudaMalloc(&d_spans, max_spans * sizeof(uint2)));
-    BVH_TRY(cudaMalloc(&d_axis, max_spans * 4));
-    BVH_TRY(cudaMalloc(&d_sbox, max_spans * 48));
+    BVH_TRY(grt_dev_alloc((void**)&d_boxes, (size_t)n * 48));
+    BVH_TRY(grt_dev_alloc((void**)&d_order, (size_t)n * 4));
+    BVH_TRY(grt_dev_alloc((void**)&d_span_of, (size_t)n * 4));
+    BVH_TRY(grt_dev_alloc((void**)&d_keys, (size_t)n * sizeof(SortKey)));
+    BVH_TRY(grt_dev_alloc((void**)&d_spans, max_spans * sizeof(uint2)));
+    BVH_TRY(grt_dev_alloc((void**)&d_axis, max_spans * 4));
+    BVH_TRY(grt_dev_alloc((void**)&d_sbox, max_spans * 48));
     BVH_TRY(cub::DeviceMergeSort::StableSortPairs(nullptr, temp_bytes, d_keys, d_order, (int64_t)n, SortLess()));
-    BVH_TRY(cudaMalloc(&d_temp, temp_bytes ? temp_bytes : 16));
+    BVH_TRY(grt_dev_alloc((void**)&d_temp, temp_bytes ? temp_bytes : 16));
     BVH_TRY(cudaMemcpy(d_boxes, boxes, (size_t)n * 48, cudaMemcpyHostToDevice));
     bvh_iota<<<B, T>>>(d_order, n);
     launches++;
@@ -213,7 +213,7 @@ extern "C" int grt_bvh_order(const double* boxes, uint32_t n, int device, uint32
     BVH_TRY(cudaGetLastError());
     BVH_TRY(cudaMemcpy(order_out, d_order, (size_t)n * 4, cudaMemcpyDeviceToHost));
 done:
-    cudaFree(d_boxes); cudaFree(d_order); cudaFree(d_order2); cudaFree(d_span_of); cudaFree(d_keys); cudaFree(d_spans); cudaFree(d_axis); cudaFree(d_sbox); cudaFree(d_temp);
+    grt_dev_free(d_boxes); grt_dev_free(d_order); grt_dev_free(d_span_of); grt_dev_free(d_keys); grt_dev_free(d_spans); grt_dev_free(d_axis); grt_dev_free(d_sbox); grt_dev_free(d_temp);
     cudaSetDevice(prev_dev);
     grt_count_launch(launches);
     return rc;

@@ -35,6 +35,12 @@ const grtd::DevScene* grt_internal_dev_scene(GrtSceneHandle h);
 int grt_internal_sm_count(GrtSceneHandle h);
 int grt_internal_staged(GrtSceneHandle h);   // 0 none, 1 hot arrays, 2 whole blob
 unsigned int* grt_internal_counter(GrtSceneHandle h);
+/* Device memory from the device's stream-ordered pool, kept by the process instead of being handed back to the driver
+   on free: on the B200 boxes a cudaFree costs 30-500 ms once a process holds a few GB, which made scene upload + free
+   the largest item of an end-to-end step after the kernel itself.  grt_dev_free waits for the device first (what
+   cudaFree does implicitly). */
+cudaError_t grt_dev_alloc(void** p, size_t bytes);
+void grt_dev_free(void* p);
 /* the wavefront variant's path pool (grown on demand, freed with the scene) and 64 pinned bytes for its counters */
 void* grt_internal_wf_pool(GrtSceneHandle h, size_t bytes, void** pinned64);
 int grt_make_dev_camera(const GrtCamera* c, grtd::DevCamera* out);

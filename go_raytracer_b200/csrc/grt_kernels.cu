@@ -33,6 +33,33 @@ static thread_local std::string g_last_error;
 static std::atomic<uint64_t> g_launches(0);
 
 void grt_set_error(const std::string& s) { g_last_error = s; }
+
+cudaError_t grt_dev_alloc(void** p, size_t bytes) {
+    *p = nullptr;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    static std::mutex m;
+    static bool tuned[64] = {false};
+    {
+        std::lock_guard<std::mutex> lk(m);
+        if (dev < 64 && !tuned[dev]) {   // keep freed blocks in the pool instead of returning them to the driver
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                unsigned long long keep = ~0ull;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            tuned[dev] = true;
+        }
+    }
+    if ((e = cudaMallocAsync(p, bytes ? bytes : 1, 0)) != cudaSuccess) return e;
+    return cudaStreamSynchronize(0);
+}
+void grt_dev_free(void* p) {
+    if (!p) return;
+    cudaDeviceSynchronize();
+    cudaFreeAsync(p, 0);
+}
 void grt_count_launch(uint64_t n) { g_launches += n; }
 
 #define CUDA_TRY(call)                                                                          \
@@ -614,7 +641,7 @@ extern "C" int grt_scene_upload(const GrtScene* s, int device, GrtSceneHandle* o
     auto upload = [&](void** dptr, const void* src, size_t bytes) -> int {
         *dptr = nullptr;
         if (!bytes) return GRT_OK;
-        CUDA_TRY(cudaMalloc(dptr, bytes));
+        CUDA_TRY(grt_dev_alloc(dptr, bytes));
         CUDA_TRY(cudaMemcpy(*dptr, src, bytes, cudaMemcpyHostToDevice));
         return GRT_OK;
     };
@@ -630,11 +657,9 @@ extern "C" int grt_scene_upload(const GrtScene* s, int device, GrtSceneHandle* o
     ds.tri_v64 = (const double*)h->d_tri_v64;
     ds.texels = (const uint8_t*)h->d_texels;
     ds.perlins = (const GrtPerlin*)h->d_perlins;
-    CUDA_TRY(cudaMalloc((void**)&h->d_counter, 256));
+    CUDA_TRY(grt_dev_alloc((void**)&h->d_counter, 256));
     h->staged = ds.stage_bytes == 0 ? 0 : (ds.stage_bytes == ds.blob_bytes ? 2 : 1);
-    cudaDeviceProp prop;
-    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-    h->sm_count = prop.multiProcessorCount;
+    CUDA_TRY(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));   // (cudaGetDeviceProperties takes milliseconds)
     *out = h;
     return GRT_OK;
 }
@@ -642,8 +667,8 @@ extern "C" int grt_scene_upload(const GrtScene* s, int device, GrtSceneHandle* o
 extern "C" int grt_scene_free(GrtSceneHandle h) {
     if (!h) return GRT_OK;
     cudaSetDevice(h->device);
-    cudaFree(h->d_blob); cudaFree(h->d_tris); cudaFree(h->d_tri_shade); cudaFree(h->d_tri_v64); cudaFree(h->d_texels); cudaFree(h->d_perlins); cudaFree(h->d_counter);
-    if (h->wf_pool) cudaFree(h->wf_pool);
+    grt_dev_free(h->d_blob); grt_dev_free(h->d_tris); grt_dev_free(h->d_tri_shade); grt_dev_free(h->d_tri_v64); grt_dev_free(h->d_texels); grt_dev_free(h->d_perlins); grt_dev_free(h->d_counter);
+    grt_dev_free(h->wf_pool);
     if (h->wf_pinned) cudaFreeHost(h->wf_pinned);
     delete h;
     return GRT_OK;
@@ -655,8 +680,8 @@ int grt_internal_staged(GrtSceneHandle h) { return h->staged; }
 unsigned int* grt_internal_counter(GrtSceneHandle h) { return h->d_counter; }
 void* grt_internal_wf_pool(GrtSceneHandle h, size_t bytes, void** pinned64) {
     if (bytes > h->wf_pool_bytes) {
-        if (h->wf_pool) { cudaFree(h->wf_pool); h->wf_pool = nullptr; h->wf_pool_bytes = 0; }
-        if (cudaMalloc(&h->wf_pool, bytes) != cudaSuccess) { h->wf_pool = nullptr; return nullptr; }
+        if (h->wf_pool) { grt_dev_free(h->wf_pool); h->wf_pool = nullptr; h->wf_pool_bytes = 0; }
+        if (grt_dev_alloc(&h->wf_pool, bytes) != cudaSuccess) { h->wf_pool = nullptr; return nullptr; }
         h->wf_pool_bytes = bytes;
     }
     if (!h->wf_pinned && cudaMallocHost(&h->wf_pinned, 64) != cudaSuccess) { h->wf_pinned = nullptr; return nullptr; }
@@ -700,9 +725,9 @@ extern "C" int grt_trace_batch(GrtSceneHandle h, const GrtRay* rays, uint64_t n,
     if (n == 0) return GRT_OK;
     CUDA_TRY(cudaSetDevice(h->device));
     GrtRay* d_rays = nullptr; GrtHit* d_hits = nullptr;
-    CUDA_TRY(cudaMalloc((void**)&d_rays, n * sizeof(GrtRay)));
-    cudaError_t e = cudaMalloc((void**)&d_hits, n * sizeof(GrtHit));
-    if (e != cudaSuccess) { cudaFree(d_rays); grt_set_error(cudaGetErrorString(e)); return GRT_E_CUDA; }
+    CUDA_TRY(grt_dev_alloc((void**)&d_rays, n * sizeof(GrtRay)));
+    cudaError_t e = grt_dev_alloc((void**)&d_hits, n * sizeof(GrtHit));
+    if (e != cudaSuccess) { grt_dev_free(d_rays); grt_set_error(cudaGetErrorString(e)); return GRT_E_CUDA; }
     int rc = GRT_OK;
     do {
         if ((e = cudaMemcpy(d_rays, rays, n * sizeof(GrtRay), cudaMemcpyHostToDevice)) != cudaSuccess) break;
@@ -711,7 +736,7 @@ extern "C" int grt_trace_batch(GrtSceneHandle h, const GrtRay* rays, uint64_t n,
         if ((e = cudaDeviceSynchronize()) != cudaSuccess) break;
         if ((e = cudaMemcpy(hits, d_hits, n * sizeof(GrtHit), cudaMemcpyDeviceToHost)) != cudaSuccess) break;
     } while (0);
-    cudaFree(d_rays); cudaFree(d_hits);
+    grt_dev_free(d_rays); grt_dev_free(d_hits);
     if (e != cudaSuccess) { grt_set_error(cudaGetErrorString(e)); return GRT_E_CUDA; }
     return rc;
 }
@@ -835,10 +860,10 @@ extern "C" int grt_render(GrtSceneHandle h, const GrtCamera* cam, const GrtOptio
     int rc = GRT_OK;
     cudaError_t e = cudaSuccess;
     do {
-        if ((e = cudaMalloc((void**)&d_sum, nval * sizeof(float))) != cudaSuccess) break;
+        if ((e = grt_dev_alloc((void**)&d_sum, nval * sizeof(float))) != cudaSuccess) break;
         if ((e = cudaMemcpy(d_sum, rgb_sum, nval * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess) break;
         if (stats) {
-            if ((e = cudaMalloc((void**)&d_stats, sizeof(GrtStats))) != cudaSuccess) break;
+            if ((e = grt_dev_alloc((void**)&d_stats, sizeof(GrtStats))) != cudaSuccess) break;
             if ((e = cudaMemset(d_stats, 0, sizeof(GrtStats))) != cudaSuccess) break;
         }
         GrtOptions o = *opt;
@@ -846,7 +871,7 @@ extern "C" int grt_render(GrtSceneHandle h, const GrtCamera* cam, const GrtOptio
         rc = grt_render_device(h, cam, &o, d_sum, nullptr, d_stats);
         if (rc) break;
         if (rgb8) {
-            if ((e = cudaMalloc((void**)&d_rgb8, nval)) != cudaSuccess) break;
+            if ((e = grt_dev_alloc((void**)&d_rgb8, nval)) != cudaSuccess) break;
             float scale = 1.0f / (float)((double)cam->spp_sqrt * (double)cam->spp_sqrt);
             rc = grt_tonemap_device(d_sum, d_rgb8, nval, scale, nullptr);
             if (rc) break;
@@ -856,7 +881,7 @@ extern "C" int grt_render(GrtSceneHandle h, const GrtCamera* cam, const GrtOptio
         if (rgb8 && (e = cudaMemcpy(rgb8, d_rgb8, nval, cudaMemcpyDeviceToHost)) != cudaSuccess) break;
         if (stats && (e = cudaMemcpy(stats, d_stats, sizeof(GrtStats), cudaMemcpyDeviceToHost)) != cudaSuccess) break;
     } while (0);
-    cudaFree(d_sum); cudaFree(d_rgb8); cudaFree(d_stats);
+    grt_dev_free(d_sum); grt_dev_free(d_rgb8); grt_dev_free(d_stats);
     if (e != cudaSuccess) { grt_set_error(std::string("grt_render: ") + cudaGetErrorString(e)); return GRT_E_CUDA; }
     return rc;
 }

@@ -79,7 +79,7 @@ extern "C" int grt_render_multi(const GrtScene* scene, const GrtCamera* cam, con
         CU(cudaStreamCreateWithFlags(&st[g], cudaStreamNonBlocking));
         CU(cudaEventCreate(&e0[g]));
         CU(cudaEventCreate(&e1[g]));
-        CU(cudaMalloc((void**)&d_sum[g], nval * sizeof(float)));
+        CU(grt_dev_alloc((void**)&d_sum[g], nval * sizeof(float)));
         if (g == 0) CU(cudaMemcpyAsync(d_sum[g], rgb_sum, nval * sizeof(float), cudaMemcpyHostToDevice, st[g]));
         else CU(cudaMemsetAsync(d_sum[g], 0, nval * sizeof(float), st[g]));
     }
@@ -111,7 +111,7 @@ extern "C" int grt_render_multi(const GrtScene* scene, const GrtCamera* cam, con
     }
     CU(cudaSetDevice(devices[0]));
     if (rgb8) {
-        CU(cudaMalloc((void**)&d_rgb8, nval));
+        CU(grt_dev_alloc((void**)&d_rgb8, nval));
         float scale = 1.0f / (float)((double)cam->spp_sqrt * (double)cam->spp_sqrt);
         rc = grt_tonemap_device(d_sum[0], d_rgb8, nval, scale, st[0]);
         if (rc) goto done;
@@ -135,12 +135,12 @@ done:
     for (int g = 0; g < n; g++) {
         if (hs[g]) cudaSetDevice(devices[g]);
         if (comms_ok && comms[g]) g_nccl.CommDestroy(comms[g]);
-        if (d_sum[g]) cudaFree(d_sum[g]);
+        if (d_sum[g]) grt_dev_free(d_sum[g]);
         if (e0[g]) cudaEventDestroy(e0[g]);
         if (e1[g]) cudaEventDestroy(e1[g]);
         if (st[g]) cudaStreamDestroy(st[g]);
         if (hs[g]) grt_scene_free(hs[g]);
     }
-    if (d_rgb8) { cudaSetDevice(devices[0]); cudaFree(d_rgb8); }
+    if (d_rgb8) { cudaSetDevice(devices[0]); grt_dev_free(d_rgb8); }
     return rc;
 }
