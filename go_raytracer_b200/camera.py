@@ -74,6 +74,28 @@ class DeviceScene:
                                            float(scale), C.c_void_p(stream_ptr)))
 
 
+def write_p6(rgb8):
+    """Binary PPM of the same pixels."""
+    rgb8 = np.ascontiguousarray(rgb8, dtype=np.uint8)
+    h, w, _ = rgb8.shape
+    buf = C.create_string_buffer(32 + w * h * 3)
+    n = N.lib().grt_host_write_p6(rgb8.ctypes.data, w, h, buf, len(buf))
+    if n < 0:
+        raise ValueError("grt_host_write_p6 failed")
+    return buf.raw[:n]
+
+
+def write_png(rgb8):
+    """PNG (8-bit RGB, stored deflate blocks) of the same pixels."""
+    rgb8 = np.ascontiguousarray(rgb8, dtype=np.uint8)
+    h, w, _ = rgb8.shape
+    buf = C.create_string_buffer(256 + (3 * w + 1) * h + 5 * ((3 * w + 1) * h // 65535 + 2))
+    n = N.lib().grt_host_write_png(rgb8.ctypes.data, w, h, buf, len(buf))
+    if n < 0:
+        raise ValueError("grt_host_write_png failed")
+    return buf.raw[:n]
+
+
 def write_ppm(rgb8):
     """P3 text exactly as camera.go:160 + color.go:45 produce it."""
     rgb8 = np.ascontiguousarray(rgb8, dtype=np.uint8)

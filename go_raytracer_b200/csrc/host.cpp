@@ -188,8 +188,74 @@ long grt_host_write_ppm(const uint8_t* rgb8, int width, int height, char* out, l
     return n;
 }
 
+long grt_host_write_p6(const uint8_t* rgb8, int width, int height, unsigned char* out, long cap) {
+    if (!rgb8 || !out || cap < 32) return -1;
+    long n = snprintf((char*)out, (size_t)cap, "P6\n%d %d\n255\n", width, height);
+    const long body = (long)width * height * 3;
+    if (n + body > cap) return -1;
+    memcpy(out + n, rgb8, (size_t)body);
+    return n + body;
+}
+
+// PNG (RFC 2083) with the scanlines in stored (uncompressed) deflate blocks: no compressor in the image, and the point
+// is an exact, viewer-readable container for the same bytes the P3 text carries.
+long grt_host_write_png(const uint8_t* rgb8, int width, int height, unsigned char* out, long cap) {
+    if (!rgb8 || !out || width <= 0 || height <= 0) return -1;
+    static uint32_t crc_table[256];
+    static bool have_table = false;
+    if (!have_table) {
+        for (uint32_t i = 0; i < 256; i++) { uint32_t c = i; for (int k = 0; k < 8; k++) c = (c & 1u) ? 0xEDB88320u ^ (c >> 1) : c >> 1; crc_table[i] = c; }
+        have_table = true;
+    }
+    const size_t row = (size_t)width * 3 + 1, raw = row * (size_t)height;
+    const size_t n_blocks = (raw + 65534) / 65535;
+    const size_t zlen = 2 + raw + 5 * n_blocks + 4;
+    const size_t total = 8 + (12 + 13) + (12 + zlen) + 12;
+    if ((size_t)cap < total) return -1;
+    unsigned char* p = out;
+    auto be32 = [](unsigned char* q, uint32_t v) { q[0] = (unsigned char)(v >> 24); q[1] = (unsigned char)(v >> 16); q[2] = (unsigned char)(v >> 8); q[3] = (unsigned char)v; };
+    auto chunk_end = [&](unsigned char* type_at, size_t len) {   // CRC over type + data
+        uint32_t c = 0xFFFFFFFFu;
+        for (size_t i = 0; i < len + 4; i++) c = crc_table[(c ^ type_at[i]) & 0xFFu] ^ (c >> 8);
+        be32(type_at + 4 + len, c ^ 0xFFFFFFFFu);
+    };
+    static const unsigned char sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
+    memcpy(p, sig, 8); p += 8;
+    be32(p, 13); memcpy(p + 4, "IHDR", 4); be32(p + 8, (uint32_t)width); be32(p + 12, (uint32_t)height);
+    p[16] = 8; p[17] = 2; p[18] = 0; p[19] = 0; p[20] = 0;   // 8 bits, RGB, deflate, no filter method, no interlace
+    chunk_end(p + 4, 13); p += 12 + 13;
+    be32(p, (uint32_t)zlen); memcpy(p + 4, "IDAT", 4);
+    unsigned char* z = p + 8;
+    *z++ = 0x78; *z++ = 0x01;
+    uint32_t a1 = 1, a2 = 0;   // Adler-32 of the raw scanline stream
+    size_t done = 0, y = 0, x = 0;   // position in the raw stream = filter byte + row bytes
+    for (size_t b = 0; b < n_blocks; b++) {
+        const size_t len = raw - done < 65535 ? raw - done : 65535;
+        *z++ = (b + 1 == n_blocks) ? 1 : 0;
+        *z++ = (unsigned char)(len & 0xFF); *z++ = (unsigned char)(len >> 8);
+        *z++ = (unsigned char)(~len & 0xFF); *z++ = (unsigned char)((~len >> 8) & 0xFF);
+        for (size_t i = 0; i < len; i++) {
+            unsigned char v = (x == 0) ? 0 : rgb8[y * (size_t)width * 3 + (x - 1)];   // filter type 0 (None) starts every row
+            *z++ = v;
+            a1 += v; if (a1 >= 65521u) a1 -= 65521u;
+            a2 += a1; if (a2 >= 65521u) a2 -= 65521u;
+            if (++x == row) { x = 0; y++; }
+        }
+        done += len;
+    }
+    be32(z, (a2 << 16) | a1);
+    chunk_end(p + 4, zlen); p += 12 + zlen;
+    be32(p, 0); memcpy(p + 4, "IEND", 4); chunk_end(p + 4, 0); p += 12;
+    return (long)(p - out);
+}
+
 int grt_host_camera_render(GrtHostScene* s, const GrtCameraConfig* cfg, uint64_t seed, int variant, int n_gpus,
                            float* rgb_sum_out, char* ppm_out, long ppm_cap, long* ppm_len, double* kernel_ms) {
+    return grt_host_camera_render_rgb8(s, cfg, seed, variant, n_gpus, rgb_sum_out, nullptr, ppm_out, ppm_cap, ppm_len, kernel_ms);
+}
+
+int grt_host_camera_render_rgb8(GrtHostScene* s, const GrtCameraConfig* cfg, uint64_t seed, int variant, int n_gpus,
+                                float* rgb_sum_out, uint8_t* rgb8_out, char* ppm_out, long ppm_cap, long* ppm_len, double* kernel_ms) {
     if (!s || !cfg) { fail("NULL argument"); return GRT_E_INVALID; }
     GrtScene scene;
     if (grt_host_flatten(s, &scene)) return GRT_E_INVALID;
@@ -216,6 +282,7 @@ int grt_host_camera_render(GrtHostScene* s, const GrtCameraConfig* cfg, uint64_t
     }
     if (rc) { fail(grt_last_error()); return rc; }
     if (rgb_sum_out) memcpy(rgb_sum_out, sum.data(), nval * sizeof(float));
+    if (rgb8_out) memcpy(rgb8_out, rgb8.data(), nval);
     if (ppm_out) {
         long n = grt_host_write_ppm(rgb8.data(), cam.width, cam.height, ppm_out, ppm_cap);
         if (n < 0) { fail("ppm buffer too small"); return GRT_E_INVALID; }

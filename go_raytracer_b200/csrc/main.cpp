@@ -49,10 +49,20 @@ int main(int argc, char** argv) {
     if (h < 1) h = 1;
     long cap = 32 + (long)cam.Width * h * 12;
     std::vector<char> ppm((size_t)cap);
+    std::vector<uint8_t> rgb8((size_t)cam.Width * h * 3);
     long len = 0;
     double ms = 0;
-    int rc = grt_host_camera_render(s, &cam, 0xC0FFEEull, variant, gpus, nullptr, ppm.data(), cap, &len, &ms);
+    // the reference writes P3 text whatever the file is called; ".png" / ".pnm" ask for the binary containers instead
+    auto ends_with = [&](const char* e) { size_t n = strlen(e); return outFile.size() >= n && outFile.compare(outFile.size() - n, n, e) == 0; };
+    const bool png = ends_with(".png"), p6 = ends_with(".pnm");
+    int rc = grt_host_camera_render_rgb8(s, &cam, 0xC0FFEEull, variant, gpus, nullptr, rgb8.data(), (png || p6) ? nullptr : ppm.data(), cap, &len, &ms);
     if (rc) { fprintf(stderr, "render failed (%d): %s / %s\n", rc, grt_host_last_error(), grt_last_error()); fclose(f); return 1; }
+    if (png || p6) {
+        std::vector<unsigned char> bin(rgb8.size() + rgb8.size() / 1000 + (size_t)h * 8 + 256);
+        len = png ? grt_host_write_png(rgb8.data(), cam.Width, h, bin.data(), (long)bin.size()) : grt_host_write_p6(rgb8.data(), cam.Width, h, bin.data(), (long)bin.size());
+        if (len < 0) { fprintf(stderr, "image encode failed\n"); fclose(f); return 1; }
+        fwrite(bin.data(), 1, (size_t)len, f);
+    } else
     fwrite(ppm.data(), 1, (size_t)len, f);   // main.go:479
     fclose(f);
     grt_host_scene_free(s);

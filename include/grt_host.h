@@ -97,6 +97,11 @@ int grt_host_flatten_opts(GrtHostScene* s, int collapse_whole, int collapse_leaf
 int grt_host_camera_derive(const GrtCameraConfig* cfg, GrtCamera* out);
 /* P3 text exactly as camera.go:160 + color.go:45 write it; returns bytes written or -1. */
 long grt_host_write_ppm(const uint8_t* rgb8, int width, int height, char* out, long cap);
+/* The same pixels in binary containers (the reference's README lists other output formats as future work,
+ * README.md:63): P6 ("P6\n%d %d\n255\n" + raw RGB) and PNG (8-bit RGB, stored deflate blocks; cap >= 100 + 1.001 *
+ * (3*width+1)*height).  Return bytes written or -1. */
+long grt_host_write_p6(const uint8_t* rgb8, int width, int height, unsigned char* out, long cap);
+long grt_host_write_png(const uint8_t* rgb8, int width, int height, unsigned char* out, long cap);
 
 /* Camera.Render(world, lights) behind the CUDA backend: flatten, upload, render
  * on n_gpus devices (strata split + ncclReduce when n_gpus > 1), tonemap, P3
@@ -104,6 +109,10 @@ long grt_host_write_ppm(const uint8_t* rgb8, int width, int height, char* out, l
  * per-pixel radiance sums.  Returns 0 or a GRT_E_* code. */
 int grt_host_camera_render(GrtHostScene* s, const GrtCameraConfig* cfg, uint64_t seed, int variant, int n_gpus,
                            float* rgb_sum_out, char* ppm_out, long ppm_cap, long* ppm_len, double* kernel_ms);
+
+/* Same, also handing back the quantised pixels (rgb8_out: width*height*3 bytes, may be NULL). */
+int grt_host_camera_render_rgb8(GrtHostScene* s, const GrtCameraConfig* cfg, uint64_t seed, int variant, int n_gpus,
+                                float* rgb_sum_out, uint8_t* rgb8_out, char* ppm_out, long ppm_cap, long* ppm_len, double* kernel_ms);
 
 /* Opaque pointer to the scene description, consumed by the test oracle only. */
 const void* grt_host_scene_description(GrtHostScene* s);

@@ -133,6 +133,29 @@ def test_render_statistical_parity_independent_seeds():
     assert abs(gm.mean() - om.mean()) <= 4 * np.sqrt((2 * var / S2).sum()) / gm.size + 1e-4
 
 
+def test_render_statistical_parity_at_headline_sample_count():
+    """The north star's image bar at the headline's 4096 spp (64 x 64 strata), independent streams on the two sides:
+    >= 99.7 % of pixel-channels within 3 sigma of the Monte Carlo bound and mean RGB error <= 1e-3.  Both variants."""
+    import os
+    s, cfg = g.builtin_scene(6, width=96, spp=4096)
+    cam = g.derive_camera(cfg)
+    S2 = cam.spp_sqrt ** 2
+    assert S2 == 4096
+    os_, osq, _, _ = O.OracleWorld(s).render(cfg, seed=0xC0FFEE, want_sumsq=True, nthreads=os.cpu_count() or 1)
+    om = os_ / S2
+    var = np.maximum(osq / S2 - om ** 2, 1e-12)
+    sigma = np.sqrt(2 * var / S2)
+    dev = g.DeviceScene(s)
+    for variant in (g.GRT_VARIANT_MEGAKERNEL, g.GRT_VARIANT_WAVEFRONT):
+        gs, _, _ = dev.render(cam, seed=777, variant=variant)
+        gm = gs.astype(np.float64) / S2
+        fin = np.isfinite(gm) & np.isfinite(om)
+        assert fin.mean() > 0.9999
+        within = (np.abs(gm - om)[fin] <= 3 * sigma[fin] + 1e-6).mean()
+        assert within >= 0.997, f"variant {variant}: only {within:.4f} of pixel-channels within 3 sigma"
+        assert abs(gm[fin].mean() - om[fin].mean()) <= 1e-3, f"variant {variant}: mean RGB error {abs(gm[fin].mean() - om[fin].mean()):.2e}"
+
+
 def test_strata_sharding_is_exactly_additive():
     """Multi-GPU sharding splits the strata set s = g (mod G); shards must add up to the full render bit for bit
     per shard (each pixel-sample is keyed by its global index, independent of G)."""
