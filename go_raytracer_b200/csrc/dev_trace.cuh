@@ -34,6 +34,7 @@ enum : uint32_t {
 #define V_SPHERES (F_NODE | F_SPHERE | F_LIST | F_SPECULAR | F_TEXTURE | F_SPHERE_LIGHT | F_DEFOCUS)
 #define V_MESH (F_NODE | F_SPHERE | F_TRI | F_LIST | F_SPECULAR | F_SPHERE_LIGHT | F_TRI_LIGHT | F_TRISHADE | F_DEFOCUS)
 #define V_FULL F_ALL
+#define V_FULL_UNIQ (F_ALL & ~F_DUPIDS)   /* everything, quads excluded by flat ref (no duplicated quad ids) */
 #define GRT_NEEDS_F64(FEAT) (((FEAT) & F_SPHERE) != 0)
 
 // Device-internal quad records, repacked from GrtQuad at upload.

@@ -417,11 +417,12 @@ static uint32_t scan_features(const GrtScene* s) {
         if (s->lights[i].type == GRT_LIGHT_TRI) f |= F_TRI_LIGHT;
     }
     if (s->tri_shade) f |= F_TRISHADE;
-    {   // does any object id name more than one flat primitive (an object listed or instanced twice)?
+    {   // does any QUAD object id name more than one flat quad (an object listed or instanced twice)?  Spheres and
+        // triangles carry their id in the hot record and are always excluded by id; quads are excluded by flat ref
+        // unless this flag says a ref no longer identifies the object.
         std::vector<uint32_t> ids;
-        for (uint32_t i = 0; i < s->n_spheres; i++) ids.push_back(s->spheres[i].id);
+        ids.reserve(s->n_quads);
         for (uint32_t i = 0; i < s->n_quads; i++) ids.push_back(s->quads[i].id);
-        for (uint32_t i = 0; i < s->n_tris; i++) ids.push_back(s->tris[i].id);
         std::sort(ids.begin(), ids.end());
         for (size_t i = 1; i < ids.size(); i++) if (ids[i] == ids[i - 1]) { f |= F_DUPIDS; break; }
     }
@@ -839,6 +840,7 @@ extern "C" int grt_render_device(GrtSceneHandle h, const GrtCamera* cam, const G
     if ((f & ~V_SMOKE) == 0) return launch_mega<V_SMOKE>(h, P, stats, st);
     if ((f & ~V_SPHERES) == 0) return launch_mega<V_SPHERES>(h, P, stats, st);
     if ((f & ~V_MESH) == 0) return launch_mega<V_MESH>(h, P, stats, st);
+    if ((f & ~V_FULL_UNIQ) == 0) return launch_mega<V_FULL_UNIQ>(h, P, stats, st);
     return launch_mega<V_FULL>(h, P, stats, st);
 }
 

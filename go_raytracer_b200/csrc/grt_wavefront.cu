@@ -420,6 +420,7 @@ int grt_render_wavefront(GrtSceneHandle h, const GrtCamera* cam, const GrtOption
         else if (!dup && (f & ~V_SMOKE) == 0) rc = wf_run<V_SMOKE>(h, P, st, h_counters);
         else if (!dup && (f & ~V_SPHERES) == 0) rc = wf_run<V_SPHERES>(h, P, st, h_counters);
         else if (!dup && (f & ~V_MESH) == 0) rc = wf_run<V_MESH>(h, P, st, h_counters);
+        else if (!dup) rc = wf_run<V_FULL_UNIQ>(h, P, st, h_counters);
         else rc = wf_run<F_ALL>(h, P, st, h_counters);
     }
 done:
