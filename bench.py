@@ -146,6 +146,7 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version / debug lines must not share stdout with the JSON line
         dist.init_process_group("nccl", device_id=dev)
     L = g.lib()
 
