@@ -4,7 +4,9 @@
 #include <cuda_runtime.h>
 #include "../../include/grt.h"
 
+#ifndef GRT_MEGA_THREADS
 #define GRT_MEGA_THREADS 128
+#endif
 #ifndef GRT_MEGA_MIN_BLOCKS
 #define GRT_MEGA_MIN_BLOCKS 6   /* 80 registers, 24 warps/SM: measured best of 4/5/6 (profiles/README.md) */
 #endif
