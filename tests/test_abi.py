@@ -63,3 +63,64 @@ def test_no_cpu_fallback_without_device():
 def test_ppm_writer_format():
     rgb = np.array([[[0, 255, 255], [1, 20, 100]]], dtype=np.uint8)
     assert g.write_ppm(rgb) == b"P3\n2 1\n255\n0 255 255\n1 20 100\n"      # camera.go:160, color.go:45
+
+
+C_CLIENT = r"""
+/* A plain C99 client of the boundary: what a cgo binding compiles against (INTEGRATION.md). */
+#include <stdio.h>
+#include <string.h>
+#include "grt.h"
+#include "grt_host.h"
+int main(void) {
+    if (grt_abi_version() != 1) return 10;
+    GrtHostScene* s = grt_host_scene_new();
+    GrtCameraConfig cam;
+    GrtSceneOptions so;
+    memset(&so, 0, sizeof so);
+    so.width = 8; so.spp = 4;
+    if (grt_host_builtin_scene(s, 6, &so, &cam)) return 11;          /* cornellBox, main.go:278 */
+    GrtScene flat;
+    if (grt_host_flatten(s, &flat)) return 12;
+    if (flat.n_quads != 18 || flat.n_boxes != 2 || flat.n_lights != 1) return 13;
+    GrtCamera dc;
+    if (grt_host_camera_derive(&cam, &dc)) return 14;
+    if (dc.width != 8 || dc.height != 8 || dc.spp_sqrt != 2 || dc.max_depth != 50) return 15;
+    int ndev = grt_device_count();
+    GrtSceneHandle h = 0;
+    int rc = grt_scene_upload(&flat, 0, &h);
+    if (ndev == 0) {                                                   /* no CPU fallback: a status code and a message */
+        if (rc != GRT_E_NO_DEVICE || !grt_last_error()[0]) return 16;
+    } else {
+        if (rc) return 17;
+        float sum[8 * 8 * 3]; unsigned char rgb[8 * 8 * 3];
+        GrtOptions opt;
+        memset(&opt, 0, sizeof opt); memset(sum, 0, sizeof sum);
+        opt.seed = 0xC0FFEEull; opt.sample_stride = 1; opt.variant = GRT_VARIANT_AUTO;
+        if (grt_render(h, &dc, &opt, sum, rgb, 0)) return 18;
+        float m = 0; for (int i = 0; i < 8 * 8 * 3; i++) m += sum[i];
+        if (!(m > 0)) return 19;
+        grt_scene_free(h);
+    }
+    grt_host_scene_free(s);
+    printf("c client ok (%d device%s)\n", ndev, ndev == 1 ? "" : "s");
+    return 0;
+}
+"""
+
+
+def test_plain_c99_client_compiles_links_and_runs(tmp_path):
+    """include/*.h are C headers (no C++ in the signatures) and the library is usable from plain C: builds a C99
+    client with gcc, links it against libgrt_cuda.so and runs it.  On a GPU box the client also renders."""
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    src = tmp_path / "client.c"
+    src.write_text(C_CLIENT)
+    exe = tmp_path / "client"
+    libdir = os.path.dirname(N.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           str(src), "-o", str(exe), "-L", libdir, "-lgrt_cuda", f"-Wl,-rpath,{libdir}"])
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, f"C client failed with code {r.returncode}: {r.stdout} {r.stderr}"
+    assert "c client ok" in r.stdout

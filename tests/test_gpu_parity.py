@@ -156,6 +156,32 @@ def test_render_statistical_parity_at_headline_sample_count():
         assert abs(gm[fin].mean() - om[fin].mean()) <= 1e-3, f"variant {variant}: mean RGB error {abs(gm[fin].mean() - om[fin].mean()):.2e}"
 
 
+def test_full_size_headline_config_properties():
+    """BASELINE.json's full headline size (Cornell box 1024 x 1024 x 4096 spp, 4.3e9 paths) through size-independent
+    properties: every pixel finite, two strata shards add up to the whole, the same render twice is bit-identical, and
+    the image mean agrees with the oracle's (1024 x 1024 at 16 spp, an unbiased estimate of the same mean) inside the
+    Monte Carlo bound."""
+    import os
+    s, cfg = g.builtin_scene(6, width=1024, spp=4096)
+    cam = g.derive_camera(cfg)
+    S2 = cam.spp_sqrt ** 2
+    assert (cam.width, cam.height, S2) == (1024, 1024, 4096)
+    dev = g.DeviceScene(s)
+    full, _, _ = dev.render(cam)
+    again, _, _ = dev.render(cam)
+    assert np.isfinite(full).all() and np.array_equal(full, again)
+    halves = [dev.render(cam, sample_first=k, sample_stride=2)[0].astype(np.float64) for k in range(2)]
+    assert np.allclose(halves[0] + halves[1], full, rtol=3e-6, atol=1e-4)
+    gm = full.astype(np.float64) / S2
+    s16, cfg16 = g.builtin_scene(6, width=1024, spp=16)
+    osum, osq, _, _ = O.OracleWorld(s16).render(cfg16, seed=0xC0FFEE, want_sumsq=True, nthreads=os.cpu_count() or 1)
+    om = osum / 16.0
+    var_pix = np.maximum(osq / 16.0 - om ** 2, 0.0) / 16.0          # variance of each oracle pixel mean
+    sigma_mean = np.sqrt(var_pix.sum()) / om.size
+    assert abs(gm.mean() - om.mean()) <= 4 * sigma_mean + 1e-4, (gm.mean(), om.mean(), sigma_mean)
+    assert abs(gm.mean() - om.mean()) <= 1e-3                       # the north star's mean-RGB budget
+
+
 def test_strata_sharding_is_exactly_additive():
     """Multi-GPU sharding splits the strata set s = g (mod G); shards must add up to the full render bit for bit
     per shard (each pixel-sample is keyed by its global index, independent of G)."""
