@@ -158,8 +158,9 @@ def test_render_statistical_parity_at_headline_sample_count():
 
 def test_full_size_headline_config_properties():
     """BASELINE.json's full headline size (Cornell box 1024 x 1024 x 4096 spp, 4.3e9 paths) through size-independent
-    properties: every pixel finite, two strata shards add up to the whole, the same render twice is bit-identical, and
-    the image mean agrees with the oracle's (1024 x 1024 at 16 spp, an unbiased estimate of the same mean) inside the
+    properties: every pixel finite, two strata shards add up to the whole, the same render twice agrees to fp32
+    summation order (which warp renders which pixel is decided by an atomic counter, and a warp's lane-to-stratum
+    assignment depends on the pixel it rendered before), and the image mean agrees with the oracle's (1024 x 1024 at 16 spp, an unbiased estimate of the same mean) inside the
     Monte Carlo bound."""
     import os
     s, cfg = g.builtin_scene(6, width=1024, spp=4096)
@@ -169,7 +170,9 @@ def test_full_size_headline_config_properties():
     dev = g.DeviceScene(s)
     full, _, _ = dev.render(cam)
     again, _, _ = dev.render(cam)
-    assert np.isfinite(full).all() and np.array_equal(full, again)
+    assert np.isfinite(full).all()
+    rel = np.abs(full.astype(np.float64) - again) / np.maximum(np.abs(full), 1.0)
+    assert rel.max() <= 2e-6, f"two renders of the same frame differ by {rel.max():.2e} relative"
     halves = [dev.render(cam, sample_first=k, sample_stride=2)[0].astype(np.float64) for k in range(2)]
     assert np.allclose(halves[0] + halves[1], full, rtol=3e-6, atol=1e-4)
     gm = full.astype(np.float64) / S2
@@ -192,7 +195,7 @@ def test_strata_sharding_is_exactly_additive():
     parts = [dev.render(cam, sample_first=k, sample_stride=4)[0] for k in range(4)]
     again = [dev.render(cam, sample_first=k, sample_stride=4)[0] for k in range(4)]
     for a, b in zip(parts, again):
-        assert np.array_equal(a, b)                                   # bit-reproducible
+        assert np.allclose(a, b, rtol=2e-6, atol=1e-6)                # reproducible up to fp32 summation order
     total = np.sum(np.stack(parts).astype(np.float64), axis=0)
     assert np.allclose(total, full, rtol=2e-6, atol=1e-6)             # same samples, fp32 summation order differs
     # and a pixel window renders the same pixels
