@@ -65,6 +65,22 @@ def test_secondary_rays_hit_ids_and_t(worlds, sid):
            f"scene {sid} secondary+self", 0.08)
 
 
+@pytest.mark.parametrize("sid", [6, 7, 1])
+def test_million_ray_batches(sid):
+    """SURVEY.md 8d's fixed ray batch: the S=1 primary rays of a 1024-wide view (2^20 rays for the square Cornell
+    scenes) plus as many secondary rays harvested from the oracle's first hits; ids exact, t to 1e-5."""
+    s, cfg = g.builtin_scene(sid, width=1024, spp=1)
+    ow, dev = O.OracleWorld(s), g.DeviceScene(s)
+    cam = O.derived_camera(cfg)
+    prim = PU.primary_batch(cfg, (0, 0, cam.width, cam.height))
+    assert len(prim) >= 500_000
+    oh = ow.trace_batch(prim, audit_eps=1e-5)
+    _check(PU.compare_hits(dev.trace_batch(prim), oh, t_rel=T_REL), f"scene {sid} 1M primary")
+    sec = PU.secondary_batch(oh, np.random.default_rng(100 + sid), time=prim["time"])
+    _check(PU.compare_hits(dev.trace_batch(sec), ow.trace_batch(sec, audit_eps=1e-5, use_exclusion=True), t_rel=T_REL),
+           f"scene {sid} 1M secondary+self", 0.08)
+
+
 def test_self_exclusion_emulates_exact_arithmetic(worlds):
     """The exclusion the integrator uses (skip the planar primitive the ray starts on; c = 0 for its sphere) gives
     on an fp32-rounded origin what the fp64 reference gives on the unrounded one."""
