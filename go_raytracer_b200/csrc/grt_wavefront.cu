@@ -86,8 +86,11 @@ __global__ void __launch_bounds__(256) wf_generate(const __grid_constant__ WfPar
 }
 
 // ---- extend + enqueue ----------------------------------------------------------------------------
+#ifndef WF_EXT_MIN_BLOCKS
+#define WF_EXT_MIN_BLOCKS 4   /* 64 registers, 32 warps/SM: best of 3/4/5 on the book scenes (C4 342 / 385 / 340 Mpaths/s) */
+#endif
 template <uint32_t FEAT, int STAGED>
-__global__ void __launch_bounds__(256) wf_extend(const __grid_constant__ WfParams P) {
+__global__ void __launch_bounds__(256, WF_EXT_MIN_BLOCKS) wf_extend(const __grid_constant__ WfParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
     SceneView sv = wf_view<STAGED>(P, smem);
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
