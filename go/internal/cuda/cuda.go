@@ -43,6 +43,25 @@ func lastError(rc C.int) error {
 	return fmt.Errorf("libgrt_cuda error %d: %s", int(rc), C.GoString(C.grt_last_error()))
 }
 
+// bvhOrder binds grt_bvh_order: BuildBVH's recursive sorts on the device (bvh.go:35-61).
+func bvhOrder(boxes []float64) ([]uint32, error) {
+	n := len(boxes) / 6
+	order := make([]uint32, n)
+	if n == 0 {
+		return order, nil
+	}
+	if rc := C.grt_bvh_order((*C.double)(unsafe.Pointer(&boxes[0])), C.uint32_t(n), 0, (*C.uint32_t)(unsafe.Pointer(&order[0]))); rc != 0 {
+		return nil, lastError(rc)
+	}
+	return order, nil
+}
+
+func init() {
+	if DeviceCount() > 0 {
+		hittable.BVHOrderHook = bvhOrder
+	}
+}
+
 // DeviceCount reports the number of usable CUDA devices (0: the backend cannot be used; there is no CPU fallback in it).
 func DeviceCount() int { return int(C.grt_device_count()) }
 
