@@ -294,7 +294,10 @@ const char* grt_last_error(void);
 
 /* Copies the flat scene to HBM on `device` (small scenes are additionally
  * staged into shared memory by the kernels).  The GrtScene may be freed after
- * the call returns. */
+ * the call returns.  A handle carries per-render scratch (the pixel counter,
+ * the wavefront path pool): run one render at a time per handle; different
+ * handles, also on one device, are independent.  Device memory comes from a
+ * process-wide pool and returns to it on grt_scene_free. */
 int grt_scene_upload(const GrtScene* scene, int device, GrtSceneHandle* out);
 int grt_scene_free(GrtSceneHandle h);
 
