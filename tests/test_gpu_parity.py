@@ -366,3 +366,24 @@ def test_auto_variant_picks_by_scene_and_keeps_the_image():
     # event counters exist only in the megakernel: asking for them keeps AUTO there
     _, _, st = dev.render(cam, variant=g.GRT_VARIANT_AUTO, want_stats=True)
     assert st["paths"] == cam.width * cam.height * cam.spp_sqrt ** 2
+
+
+@pytest.mark.parametrize("sid,w,spp", [(6, 1, 1), (6, 3, 4), (1, 2, 1), (8, 5, 4)])
+def test_tiny_frames_both_variants(sid, w, spp):
+    """Edge sizes: one pixel, one sample, fewer paths than a warp; the two variants still agree and every pixel is set
+    by exactly its own samples (the sum over sharded strata equals the whole)."""
+    kw = {"mesh_segments": 24} if sid == 8 else {}
+    s, cfg = g.builtin_scene(sid, width=w, spp=spp, **kw)
+    cam = g.derive_camera(cfg)
+    dev = g.DeviceScene(s)
+    mega, _, _ = dev.render(cam, variant=g.GRT_VARIANT_MEGAKERNEL)
+    wave, _, _ = dev.render(cam, variant=g.GRT_VARIANT_WAVEFRONT)
+    assert mega.shape == (cam.height, cam.width, 3)
+    fin = np.isfinite(mega) & np.isfinite(wave)
+    assert np.allclose(wave[fin], mega[fin], rtol=1e-4, atol=1e-4) and (np.isfinite(mega) == np.isfinite(wave)).all()
+    S2 = cam.spp_sqrt ** 2
+    if S2 > 1:
+        parts = [dev.render(cam, sample_first=k, sample_stride=S2)[0].astype(np.float64) for k in range(S2)]
+        tot = np.sum(parts, axis=0)
+        f2 = np.isfinite(tot) & np.isfinite(mega)
+        assert np.allclose(tot[f2], mega[f2], rtol=1e-5, atol=1e-5)
