@@ -123,6 +123,7 @@ struct RenderParams {
     int x0, y0, ww, wh;                            // pixel window
     uint32_t n_pixels;                             // ww * wh
     uint32_t claim;                                // pixels claimed per atomicAdd
+    int atomic_sum;                                // rgb_sum is shared with other renders / peer GPUs: accumulate with system-scope atomics
     int trav_exit16;                               // a traversal slice ends when fewer than trav_exit16/16 of its lanes have work left
     float* rgb_sum;                                // device, W*H*3, += per pixel
     unsigned int* counter;
@@ -267,7 +268,11 @@ __global__ void __launch_bounds__(GRT_MEGA_THREADS, mega_min_blocks(FEAT)) rende
             if (lane == 0) {
                 int px = (int)(xy_cur & 0xffffu), py = (int)(xy_cur >> 16);
                 float* dst = P.rgb_sum + ((size_t)py * cam.width + px) * 3;
-                dst[0] += s.x; dst[1] += s.y; dst[2] += s.z;   // this warp owns the pixel for the whole launch
+                if (P.atomic_sum) {   // the buffer is shared (another GPU's shard over NVLink peer memory, grt_multi.cu)
+                    atomicAdd_system(dst, s.x); atomicAdd_system(dst + 1, s.y); atomicAdd_system(dst + 2, s.z);
+                } else {
+                    dst[0] += s.x; dst[1] += s.y; dst[2] += s.z;   // this warp owns the pixel for the whole launch
+                }
             }
             acc0 = acc1; acc1 = mk3(0, 0, 0);
             if (active) my_parity = 0u;   // survivors were on pix_nxt
@@ -836,6 +841,7 @@ extern "C" int grt_render_device(GrtSceneHandle h, const GrtCamera* cam, const G
         P.trav_exit16 = exit16;
     }
     P.rgb_sum = d_rgb_sum;
+    P.atomic_sum = (opt->flags & GRT_OPT_ATOMIC_SUM) ? 1 : 0;
     P.counter = h->d_counter;
     P.stats = d_stats;
     CUDA_TRY(cudaMemsetAsync(h->d_counter, 0, 4, st));

@@ -1,15 +1,20 @@
 // grt_multi.cu — in-process multi-GPU render (the `-gpus N` path of the CLI and
 // of a cgo caller, which is ONE process).  Each device holds a scene replica
-// and renders the strata s ≡ g (mod N) into a private fp32 sum buffer; the
-// buffers are combined with ONE ncclReduce(sum, root = devices[0]) over
-// NVLink/NVSwitch before tonemap.  (bench.py instead runs one process per GPU
-// and reduces through torch.distributed's NCCL communicator.)
+// and renders the strata s ≡ g (mod N).
+//
+// Fused path (NVLink / NVSwitch with native peer atomics): ONE accumulation buffer lives on devices[0], every other
+// device maps it as peer memory, and the render kernels add their per-pixel sums straight into it with system-scope
+// atomics as each pixel is retired — the exchange is spread over the whole render (12.6 MB of 4-byte reductions over
+// tens of milliseconds) instead of following it, and no collective runs at all.
+// Fallback (no peer access): private buffers and ONE ncclReduce(sum, root = devices[0]) before tonemap.
+// (bench.py instead runs one process per GPU and reduces through torch.distributed's NCCL communicator.)
 //
 // NCCL is bound at run time with dlopen so that libgrt_cuda has no link-time
 // dependency on a particular libnccl (PyTorch bundles its own).
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <string.h>
+#include <stdlib.h>
 #include <string>
 #include <vector>
 #include "grt_internal.h"
@@ -60,7 +65,16 @@ extern "C" int grt_render_multi(const GrtScene* scene, const GrtCamera* cam, con
     int have = grt_device_count();
     if (have <= 0) { grt_set_error("no CUDA device available (libgrt_cuda has no CPU fallback)"); return GRT_E_NO_DEVICE; }
     for (int i = 0; i < n; i++) if (devices[i] < 0 || devices[i] >= have) { grt_set_error("device ordinal out of range"); return GRT_E_NO_DEVICE; }
-    if (n > 1 && !g_nccl.load()) { grt_set_error("libnccl.so.2 could not be loaded"); return GRT_E_NCCL; }
+    // can every other device reach devices[0]'s memory with native atomics?
+    bool fused = n > 1;
+    if (const char* e = getenv("GRT_MULTI_P2P")) fused = fused && atoi(e) != 0;
+    for (int g = 1; g < n && fused; g++) {
+        int can = 0, at = 0;
+        if (devices[g] == devices[0]) { fused = false; break; }
+        if (cudaDeviceCanAccessPeer(&can, devices[g], devices[0]) != cudaSuccess || !can) fused = false;
+        else if (cudaDeviceGetP2PAttribute(&at, cudaDevP2PAttrNativeAtomicSupported, devices[g], devices[0]) != cudaSuccess || !at) fused = false;
+    }
+    if (n > 1 && !fused && !g_nccl.load()) { grt_set_error("libnccl.so.2 could not be loaded"); return GRT_E_NCCL; }
 
     int rc = GRT_OK;
     size_t nval = (size_t)cam->width * cam->height * 3;
@@ -71,6 +85,9 @@ extern "C" int grt_render_multi(const GrtScene* scene, const GrtCamera* cam, con
     std::vector<ncclComm_t> comms(n, nullptr);
     uint8_t* d_rgb8 = nullptr;
     bool comms_ok = false;
+    float* d_shared = nullptr;      // fused path: the one accumulation buffer, plain cudaMalloc (peer-mappable) on devices[0]
+    cudaEvent_t e_init = nullptr;
+    float* d_total = nullptr;       // where the complete sums end up (on devices[0])
 
     for (int g = 0; g < n; g++) {
         rc = grt_scene_upload(scene, devices[g], &hs[g]);
@@ -79,11 +96,25 @@ extern "C" int grt_render_multi(const GrtScene* scene, const GrtCamera* cam, con
         CU(cudaStreamCreateWithFlags(&st[g], cudaStreamNonBlocking));
         CU(cudaEventCreate(&e0[g]));
         CU(cudaEventCreate(&e1[g]));
+        if (fused) {
+            if (g == 0) {
+                CU(cudaMalloc((void**)&d_shared, nval * sizeof(float)));
+                CU(cudaMemcpyAsync(d_shared, rgb_sum, nval * sizeof(float), cudaMemcpyHostToDevice, st[0]));
+                CU(cudaEventCreateWithFlags(&e_init, cudaEventDisableTiming));
+                CU(cudaEventRecord(e_init, st[0]));
+            } else {
+                cudaError_t pe = cudaDeviceEnablePeerAccess(devices[0], 0);
+                if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) { grt_set_error(std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(pe)); rc = GRT_E_CUDA; goto done; }
+                cudaGetLastError();
+                CU(cudaStreamWaitEvent(st[g], e_init, 0));   // the shared buffer is initialised before anyone adds to it
+            }
+            continue;
+        }
         CU(grt_dev_alloc((void**)&d_sum[g], nval * sizeof(float)));
         if (g == 0) CU(cudaMemcpyAsync(d_sum[g], rgb_sum, nval * sizeof(float), cudaMemcpyHostToDevice, st[g]));
         else CU(cudaMemsetAsync(d_sum[g], 0, nval * sizeof(float), st[g]));
     }
-    if (n > 1) { NC(g_nccl.CommInitAll(comms.data(), n, devices)); comms_ok = true; }
+    if (n > 1 && !fused) { NC(g_nccl.CommInitAll(comms.data(), n, devices)); comms_ok = true; }
 
     // every device renders its strata shard, concurrently
     for (int g = 0; g < n; g++) {
@@ -92,12 +123,13 @@ extern "C" int grt_render_multi(const GrtScene* scene, const GrtCamera* cam, con
         o.sample_first = opt->sample_first + (uint32_t)g * base_stride;
         o.sample_stride = base_stride * (uint32_t)n;
         o.device = devices[g];
+        if (fused) o.flags |= GRT_OPT_ATOMIC_SUM;
         CU(cudaSetDevice(devices[g]));
         CU(cudaEventRecord(e0[g], st[g]));
-        rc = grt_render_device(hs[g], cam, &o, d_sum[g], st[g], nullptr);
+        rc = grt_render_device(hs[g], cam, &o, fused ? d_shared : d_sum[g], st[g], nullptr);
         if (rc) goto done;
     }
-    if (n > 1) {
+    if (n > 1 && !fused) {
         NC(g_nccl.GroupStart());
         for (int g = 0; g < n; g++) {
             ncclResult_t r_ = g_nccl.Reduce(d_sum[g], d_sum[g], nval, ncclFloat32, ncclSum, 0, comms[g], st[g]);
@@ -110,10 +142,12 @@ extern "C" int grt_render_multi(const GrtScene* scene, const GrtCamera* cam, con
         CU(cudaEventRecord(e1[g], st[g]));
     }
     CU(cudaSetDevice(devices[0]));
+    if (fused) for (int g = 1; g < n; g++) CU(cudaStreamWaitEvent(st[0], e1[g], 0));   // every shard has landed before tonemap / read-back
+    d_total = fused ? d_shared : d_sum[0];
     if (rgb8) {
         CU(grt_dev_alloc((void**)&d_rgb8, nval));
         float scale = 1.0f / (float)((double)cam->spp_sqrt * (double)cam->spp_sqrt);
-        rc = grt_tonemap_device(d_sum[0], d_rgb8, nval, scale, st[0]);
+        rc = grt_tonemap_device(d_total, d_rgb8, nval, scale, st[0]);
         if (rc) goto done;
     }
     {
@@ -128,7 +162,7 @@ extern "C" int grt_render_multi(const GrtScene* scene, const GrtCamera* cam, con
         if (kernel_ms) *kernel_ms = worst;
     }
     CU(cudaSetDevice(devices[0]));
-    CU(cudaMemcpy(rgb_sum, d_sum[0], nval * sizeof(float), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(rgb_sum, d_total, nval * sizeof(float), cudaMemcpyDeviceToHost));
     if (rgb8) CU(cudaMemcpy(rgb8, d_rgb8, nval, cudaMemcpyDeviceToHost));
 
 done:
@@ -142,5 +176,7 @@ done:
         if (hs[g]) grt_scene_free(hs[g]);
     }
     if (d_rgb8) { cudaSetDevice(devices[0]); grt_dev_free(d_rgb8); }
+    if (e_init) cudaEventDestroy(e_init);
+    if (d_shared) { cudaSetDevice(devices[0]); cudaFree(d_shared); }
     return rc;
 }

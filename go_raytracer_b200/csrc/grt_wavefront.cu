@@ -49,6 +49,7 @@ struct WfParams {
     uint32_t* counters;               // C_WORDS
     unsigned long long* next_sample;
     float* rgb_sum;
+    int sys_atomics;                  // rgb_sum may live on a peer GPU (grt_render_multi): system-scope atomics
     int exit16;                       // wf_extend_dyn: a traversal slice ends when fewer than exit16/16 lanes have work
 };
 
@@ -230,7 +231,8 @@ __global__ void __launch_bounds__(WF_DYN_THREADS, WF_DYN_MIN_BLOCKS) wf_extend_d
 __device__ __forceinline__ void wf_finish_path(const WfParams& P, uint32_t slot, uint32_t pixel_index, f3 L) {
     if (L.x != 0.0f || L.y != 0.0f || L.z != 0.0f) {   // NaN != 0 is true: a NaN sample is accumulated (color.go:28-36)
         float* dst = P.rgb_sum + (size_t)pixel_index * 3;
-        atomicAdd(dst, L.x); atomicAdd(dst + 1, L.y); atomicAdd(dst + 2, L.z);
+        if (P.sys_atomics) { atomicAdd_system(dst, L.x); atomicAdd_system(dst + 1, L.y); atomicAdd_system(dst + 2, L.z); }
+        else { atomicAdd(dst, L.x); atomicAdd(dst + 1, L.y); atomicAdd(dst + 2, L.z); }
     }
     P.S3[slot].z = WF_FREE;
 }
@@ -443,6 +445,7 @@ int grt_render_wavefront(GrtSceneHandle h, const GrtCamera* cam, const GrtOption
     unsigned long long want = P.total < pool_slots ? P.total : pool_slots;
     P.P = (uint32_t)((want + 255) / 256 * 256);
     P.rgb_sum = d_rgb_sum;
+    P.sys_atomics = (opt->flags & GRT_OPT_ATOMIC_SUM) ? 1 : 0;
     P.exit16 = 12;
     if (const char* e = getenv("GRT_WF_EXIT16")) { int v = atoi(e); if (v >= 0 && v <= 16) P.exit16 = v; }
     void* pool = nullptr;

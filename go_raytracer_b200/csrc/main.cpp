@@ -57,6 +57,7 @@ int main(int argc, char** argv) {
     const bool png = ends_with(".png"), p6 = ends_with(".pnm");
     int rc = grt_host_camera_render_rgb8(s, &cam, 0xC0FFEEull, variant, gpus, nullptr, rgb8.data(), (png || p6) ? nullptr : ppm.data(), cap, &len, &ms);
     if (rc) { fprintf(stderr, "render failed (%d): %s / %s\n", rc, grt_host_last_error(), grt_last_error()); fclose(f); return 1; }
+    if (getenv("GRT_VERBOSE")) fprintf(stderr, "[grt_main] %d GPU(s): render + exchange %.2f ms (device time, max over devices)\n", gpus, ms);
     if (png || p6) {
         std::vector<unsigned char> bin(rgb8.size() + rgb8.size() / 1000 + (size_t)h * 8 + 256);
         len = png ? grt_host_write_png(rgb8.data(), cam.Width, h, bin.data(), (long)bin.size()) : grt_host_write_p6(rgb8.data(), cam.Width, h, bin.data(), (long)bin.size());

@@ -257,6 +257,8 @@ typedef struct GrtOptions {
     uint32_t pad;
 } GrtOptions;
 #define GRT_OPT_STATS 1u             /* fill GrtStats (slower: counts events) */
+#define GRT_OPT_ATOMIC_SUM 2u        /* accumulate into rgb_sum with system-scope atomics: several renders, also from
+                                        peer GPUs over NVLink, may then share one buffer (grt_render_multi does) */
 
 typedef struct GrtStats {            /* event counters for the roofline table */
     uint64_t paths, segments;        /* rayColor calls at depth=MaxDepth / all */

@@ -387,3 +387,33 @@ def test_tiny_frames_both_variants(sid, w, spp):
         tot = np.sum(parts, axis=0)
         f2 = np.isfinite(tot) & np.isfinite(mega)
         assert np.allclose(tot[f2], mega[f2], rtol=1e-5, atol=1e-5)
+
+
+def test_in_process_multi_gpu_matches_single_gpu():
+    """grt_render_multi (the -gpus N path of a cgo caller): strata shards of N devices accumulate into ONE buffer on the
+    first device through NVLink peer memory (system-scope atomics), or through ncclReduce without peer access; either
+    way the image is the single-GPU image up to fp32 summation order.  Needs two devices."""
+    import ctypes as C
+    import io
+    import os
+    from go_raytracer_b200 import _native as N
+    if N.lib().grt_device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    for sid, variant in ((6, g.GRT_VARIANT_MEGAKERNEL), (1, g.GRT_VARIANT_WAVEFRONT)):
+        s, cfg = g.builtin_scene(sid, width=64, spp=64)
+        cam = g.derive_camera(cfg)
+        one, _, _ = g.DeviceScene(s).render(cam, variant=variant)
+        nval = cam.width * cam.height * 3
+        for p2p in ("1", "0"):
+            os.environ["GRT_MULTI_P2P"] = p2p
+            try:
+                out = np.zeros(nval, dtype=np.float32)
+                ms = C.c_double(0)
+                rc = N.lib().grt_host_camera_render(s._h, C.byref(cfg), 0xC0FFEE, int(variant), 2, out.ctypes.data, None, 0, None, C.byref(ms))
+                N.check(rc)
+            finally:
+                os.environ.pop("GRT_MULTI_P2P", None)
+            two = out.reshape(cam.height, cam.width, 3)
+            fin = np.isfinite(one) & np.isfinite(two)
+            assert fin.mean() > 0.999
+            assert np.allclose(two[fin], one[fin], rtol=1e-4, atol=1e-4), f"scene {sid} p2p={p2p}"
