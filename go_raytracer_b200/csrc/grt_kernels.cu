@@ -828,7 +828,8 @@ extern "C" int grt_render_device(GrtSceneHandle h, const GrtCamera* cam, const G
     uint64_t paths_per_pixel = P.n_my;
     // (one claim is the unit of the end-of-frame tail: 8192 paths per claim left a 2-3 ms tail, 3 % of a 62 ms shard
     // frame at 8 GPUs; an atomic per 1024 paths is still free)
-    uint32_t claim = (uint32_t)(1024 / (paths_per_pixel ? paths_per_pixel : 1));
+    static const uint32_t claim_paths = [] { const char* e = getenv("GRT_CLAIM_PATHS"); int v = e ? atoi(e) : 0; return (uint32_t)(v > 0 ? v : 1024); }();
+    uint32_t claim = (uint32_t)(claim_paths / (paths_per_pixel ? paths_per_pixel : 1));
     if (claim < 1) claim = 1;
     if (claim > 64) claim = 64;
     // small images: every resident warp must get several claims, or most of the machine idles
