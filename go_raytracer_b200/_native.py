@@ -157,6 +157,7 @@ def lib():
         "grt_host_constant_medium": (i32, [vp, i32, dbl, i32]),
         "grt_host_set_world": (i32, [vp, i32]), "grt_host_set_lights": (i32, [vp, i32]),
         "grt_host_load_obj": (i32, [vp, C.c_char_p, C.c_char_p, P(GrtObjOptions), P(i32), P(i32), P(i32)]),
+        "grt_host_load_obj_file": (i32, [vp, C.c_char_p, P(GrtObjOptions), P(i32), P(i32), P(i32)]),
         "grt_host_builtin_scene": (i32, [vp, i32, P(GrtSceneOptions), P(GrtCameraConfig)]),
         "grt_host_flatten": (i32, [vp, P(GrtScene)]), "grt_host_flatten_opts": (i32, [vp, i32, i32, P(GrtScene)]), "grt_host_camera_derive": (i32, [P(GrtCameraConfig), P(GrtCamera)]),
         "grt_host_write_ppm": (C.c_long, [vp, i32, i32, vp, C.c_long]),
@@ -184,7 +185,7 @@ EXPORTED_SYMBOLS = [
     "grt_host_dielectric", "grt_host_diffuse_light", "grt_host_isotropic", "grt_host_sphere", "grt_host_motion_sphere",
     "grt_host_quad", "grt_host_box", "grt_host_triangle", "grt_host_list", "grt_host_list_add", "grt_host_bvh",
     "grt_host_translate", "grt_host_rotate_y", "grt_host_constant_medium", "grt_host_set_world", "grt_host_set_lights",
-    "grt_host_load_obj", "grt_host_builtin_scene", "grt_host_flatten", "grt_host_flatten_opts", "grt_host_camera_derive", "grt_host_write_ppm", "grt_host_write_p6", "grt_host_write_png", "grt_host_camera_render_rgb8",
+    "grt_host_load_obj", "grt_host_load_obj_file", "grt_host_builtin_scene", "grt_host_flatten", "grt_host_flatten_opts", "grt_host_camera_derive", "grt_host_write_ppm", "grt_host_write_p6", "grt_host_write_png", "grt_host_camera_render_rgb8",
     "grt_host_camera_render", "grt_host_scene_description",
 ]
 

@@ -4,6 +4,8 @@
 #include "scenes.hpp"
 #include <stdlib.h>
 #include <string.h>
+#include <ctype.h>
+#include <stdio.h>
 #include "flatten.hpp"
 #include "obj_loader.hpp"
 #include <cstdio>
@@ -102,6 +104,53 @@ int grt_host_load_obj(GrtHostScene* s, const char* obj_text, const char* mtl_tex
     if (lights_out) *lights_out = lr.lights;
     if (n_triangles_out) *n_triangles_out = lr.nTriangles;
     return 0;
+}
+
+// LoadObjWithOptions on a file (objLoader.go:72-140): the OBJ is read from `path`; unless IgnoreMtl is set, the first
+// `mtllib` line names the material library, looked up next to the OBJ (filepath.Join(filepath.Dir(filename), name),
+// objLoader.go:117-125).  A missing MTL file is a warning in the reference (:136-139): the default material is used.
+int grt_host_load_obj_file(GrtHostScene* s, const char* path, const GrtObjOptions* o, int* model_out, int* lights_out, int* n_triangles_out) {
+    if (!s || !path) return fail("NULL argument");
+    auto slurp = [](const std::string& p, std::string& out) -> bool {
+        FILE* f = fopen(p.c_str(), "rb");
+        if (!f) return false;
+        char buf[1 << 16];
+        size_t n;
+        while ((n = fread(buf, 1, sizeof buf, f)) > 0) out.append(buf, n);
+        fclose(f);
+        return true;
+    };
+    std::string obj, mtl;
+    if (!slurp(path, obj)) return fail(std::string("cannot open OBJ file: ") + path);   // objLoader.go:84-87
+    if (!(o && o->IgnoreMtl)) {
+        size_t pos = 0;
+        while (pos < obj.size()) {
+            size_t eol = obj.find('\n', pos);
+            if (eol == std::string::npos) eol = obj.size();
+            size_t a = pos, b = eol;
+            while (a < b && isspace((unsigned char)obj[a])) a++;
+            while (b > a && isspace((unsigned char)obj[b - 1])) b--;
+            if (b - a > 7 && obj.compare(a, 6, "mtllib") == 0 && isspace((unsigned char)obj[a + 6])) {
+                size_t c = a + 6;
+                while (c < b && isspace((unsigned char)obj[c])) c++;
+                std::string name;   // strings.Join(strings.Fields(line)[1:], " ")
+                bool gap = false;
+                for (size_t i = c; i < b; i++) {
+                    if (isspace((unsigned char)obj[i])) { gap = true; continue; }
+                    if (gap && !name.empty()) name += ' ';
+                    gap = false;
+                    name += obj[i];
+                }
+                std::string dir(path);
+                size_t slash = dir.find_last_of('/');
+                dir = slash == std::string::npos ? std::string(".") : dir.substr(0, slash);
+                slurp(dir + "/" + name, mtl);   // absent: continue with the default material
+                break;
+            }
+            pos = eol + 1;
+        }
+    }
+    return grt_host_load_obj(s, obj.c_str(), mtl.empty() ? nullptr : mtl.c_str(), o, model_out, lights_out, n_triangles_out);
 }
 
 static void toC(const grt::ir::CameraConfig& c, GrtCameraConfig* o) {

@@ -148,6 +148,21 @@ class Scene:
                                                C.byref(model), C.byref(lights), C.byref(ntri)))
         return model.value, lights.value, ntri.value
 
+    def LoadObj(self, path, **options):
+        """objLoader.LoadObjWithOptions(filename, options) on a file (objLoader.go:72): the `mtllib` the OBJ names is
+        read from the same directory.  Returns (model BVH, lights list, n triangles)."""
+        o = N.GrtObjOptions()
+        o.ScaleFactor = float(options.get("ScaleFactor", 1.0))
+        for k in ("FlipYZ", "IgnoreNormals", "FlipFaces", "IgnoreMtl", "FindWindows"):
+            setattr(o, k, int(options.get(k, False)))
+        o.Center = int(options.get("Center", True))
+        o.DefaultMaterial = int(options.get("DefaultMaterial", -1))
+        for i, v in enumerate(options.get("Position", (0, 0, 0))):
+            o.Position[i] = float(v)
+        model, lights, ntri = C.c_int(-1), C.c_int(-1), C.c_int(0)
+        N.host_check(self._L.grt_host_load_obj_file(self._h, str(path).encode(), C.byref(o), C.byref(model), C.byref(lights), C.byref(ntri)))
+        return model.value, lights.value, ntri.value
+
     def set_world(self, obj):
         N.host_check(self._L.grt_host_set_world(self._h, obj))
         self.world = obj

@@ -82,6 +82,11 @@ typedef struct GrtObjOptions {
 int grt_host_load_obj(GrtHostScene* s, const char* obj_text, const char* mtl_text, const GrtObjOptions* opt,
                       int* model_out, int* lights_out, int* n_triangles_out);
 
+/* The same from a file: `mtllib` is resolved next to the OBJ as objLoader.go:117-125 does; a missing MTL file falls
+ * back to the default material (objLoader.go:136-139). */
+int grt_host_load_obj_file(GrtHostScene* s, const char* path, const GrtObjOptions* opt,
+                           int* model_out, int* lights_out, int* n_triangles_out);
+
 /* main.go's scene functions, -S 1..8 (main.go:449-476); fills *cam like the scene function does. */
 int grt_host_builtin_scene(GrtHostScene* s, int scene_id, const GrtSceneOptions* opt, GrtCameraConfig* cam);
 

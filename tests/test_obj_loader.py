@@ -136,3 +136,33 @@ def test_model_example_goes_through_the_loader():
     # centred on Position (0, 1.8, 0), then RotateY(180) about the origin (main.go:380-384)
     p = np.concatenate([tris["v0"], tris["v0"] + tris["e0"], tris["v0"] + tris["e1"]])
     assert np.allclose((p.min(0) + p.max(0)) / 2, (0, 1.8, 0), atol=1e-5)
+
+
+def test_load_from_file_resolves_mtllib_next_to_the_obj(tmp_path):
+    """objLoader.go:84-140: the file variant reads the OBJ, takes the first `mtllib` (fields joined by one space) from
+    the OBJ's directory, and carries on with the default material when that file is missing."""
+    (tmp_path / "sub").mkdir()
+    (tmp_path / "sub" / "my lib.mtl").write_text("newmtl red\nKd 1 0 0\n")
+    objp = tmp_path / "sub" / "m.obj"
+    objp.write_text("# comment\n  mtllib   my   lib.mtl  \n" + QUAD + "usemtl red\nf 1 2 3\n")
+    sc = g.Scene()
+    model, lights, ntri = sc.LoadObj(objp, Center=False)
+    sc.set_world(sc.NewHittableList([model])); sc.set_lights(lights)
+    flat = sc.flatten(0, 0)
+    tris = as_np(flat.tris, flat.n_tris, N.TRI_DTYPE)
+    mats = as_np(flat.materials, flat.n_materials, N.MATERIAL_DTYPE)
+    texs = as_np(flat.textures, flat.n_textures, N.TEXTURE_DTYPE)
+    assert ntri == 1
+    m = mats[tris[0]["mat"]]
+    assert np.allclose(texs[m["tex"]]["color"], (1, 0, 0))          # Kd of the library next to the OBJ
+    # same result as the text entry point
+    sc2, flat2, tris2, mats2, texs2, _ = load("mtllib x.mtl\n" + QUAD + "usemtl red\nf 1 2 3\n", "newmtl red\nKd 1 0 0\n", Center=False)
+    assert np.allclose(verts(tris[0]), verts(tris2[0]))
+    # a missing library is not an error (objLoader.go:136-139)
+    obj2 = tmp_path / "n.obj"
+    obj2.write_text("mtllib nowhere.mtl\n" + QUAD + "f 1 2 3\n")
+    sc3 = g.Scene()
+    assert sc3.LoadObj(obj2)[2] == 1
+    # a missing OBJ is (objLoader.go:84-87)
+    with pytest.raises(N.GrtError):
+        g.Scene().LoadObj(tmp_path / "absent.obj")
