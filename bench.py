@@ -144,9 +144,13 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device — the backend has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # stdout carries ONE JSON line: whatever libraries print on fd 1 (NCCL's version banner does, whatever
+    # NCCL_DEBUG_FILE says) is sent to stderr; the JSON line goes out through the saved descriptor
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version / debug lines must not share stdout with the JSON line
         dist.init_process_group("nccl", device_id=dev)
     L = g.lib()
 
@@ -309,7 +313,8 @@ def run_ours(args):
                 "e2e": {"value": e2e_val, "unit": "Mpaths/s", "h2d_bytes_per_step": scene_bytes + nval * 4,
                         "d2h_bytes_per_step": nval * 4 + nval},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
