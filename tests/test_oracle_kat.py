@@ -90,3 +90,37 @@ def test_aabb_slab_semantics():
     # Go's builtin min/max propagate NaN (aabb.go:104-105): origin on a slab plane with a zero direction
     # component gives 0*Inf = NaN and the box is ACCEPTED even though the ray misses in y
     assert hit((0, 0, 0), (1, 1, 1), (0, 5, .5), (0, 0, 1), -10, 10) == 1
+
+
+# imageLoader_test.go:64-90: the 5x5 PNG fixture's exact pixel data (row-major, idx = y*Width + x)
+REF_IMG_DATA = [(209, 226, 249), (161, 176, 189), (126, 146, 139), (146, 162, 191), (214, 230, 254),
+                (124, 132, 172), (53, 64, 122), (63, 80, 105), (26, 34, 112), (154, 165, 198),
+                (83, 88, 143), (4, 13, 116), (19, 35, 120), (93, 119, 64), (94, 108, 131),
+                (138, 146, 181), (0, 0, 113), (0, 12, 114), (110, 122, 112), (140, 149, 164),
+                (220, 231, 249), (111, 122, 166), (109, 122, 166), (140, 152, 175), (215, 227, 246)]
+
+
+def test_image_texture_lookup_on_the_reference_fixture():
+    """imageTexture.Value (texture.go:70-86) over the pixel data the reference's own imageLoader test pins
+    (imageLoader_test.go:64-90): u -> |fmod(u,1)|, v -> 1 - |fmod(v,1)|, i = int(u (W-1)), j = int(v (H-1)),
+    colour = byte * (1/255).  (With this rule the last column is never sampled and the last row only at integer v.)"""
+    import go_raytracer_b200 as g
+    img = np.array(REF_IMG_DATA, dtype=np.uint8).reshape(5, 5, 3)
+    sc = g.Scene()
+    tex = sc.NewImageTextureFromArray(img)
+    lam = sc.NewTexturedLambertian(tex)
+    light = sc.NewQuad((-1, 5, -1), (2, 0, 0), (0, 0, 2), sc.NewDiffuseLight((4, 4, 4)))
+    sc.set_world(sc.NewHittableList([sc.NewQuad((0, 0, 0), (1, 0, 0), (0, 1, 0), lam), light]))
+    sc.set_lights(sc.NewHittableList([light]))
+    ow = O.OracleWorld(sc)
+    scale = 1.0 / 255.0
+    for j in range(4):
+        for i in range(4):
+            u, v = (i + 0.5) / 4.0, 1.0 - (j + 0.5) / 4.0
+            exp = np.array(REF_IMG_DATA[j * 5 + i], dtype=np.float64) * scale
+            # the texture repeats with period 1 in u and v, and a negative u mirrors: |fmod(-x, 1)| = x
+            for uu, vv in ((u, v), (u + 3.0, v), (u, v + 2.0), (-u, v)):
+                got = ow.texture_value(tex, uu, vv, (0, 0, 0))
+                assert np.array_equal(np.asarray(got), exp), (i, j, uu, vv)
+    # integer v selects the last row (v' = 1), u = 0 the first column
+    assert np.array_equal(np.asarray(ow.texture_value(tex, 0.0, 2.0, (0, 0, 0))), np.array(REF_IMG_DATA[20], dtype=np.float64) * scale)
