@@ -8,10 +8,12 @@
 // render path (camera/hittable/aabb have no *_test.go) and no Go toolchain
 // exists here, so this restatement is pinned only where the reference's own
 // unit tests reach: vec algebra, colour quantisation, interval predicates and
-// Ray.At (vec_test.go:24-154, interval_test.go:9-72, ray_test.go:11-19) —
+// Ray.At (vec_test.go:24-154, interval_test.go:9-72, ray_test.go:11-19), and the
+// image-texture lookup over the pixel data of imageLoader_test.go:64-90 —
 // checked in tests/test_oracle_kat.py.  For everything else: PARITY UNPINNED
 // by the reference; pinned instead by hand-derived known-answer cases in
-// tests/test_oracle_geometry.py.
+// tests/test_oracle_geometry.py, by the Random123 vectors for Philox, and frozen
+// against drift by tests/golden/hits_golden.npz (tests/test_golden.py).
 //
 // Every function cites the reference lines it follows (paths relative to
 // /root/reference).  Build: g++ -O2 -ffp-contract=off (Go/amd64 does not fuse
