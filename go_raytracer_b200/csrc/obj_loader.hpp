@@ -8,6 +8,8 @@
 // exiting; map_Kd / map_Ka image maps need a decoded image supplied by the caller (image decode is out of
 // scope) — without one the load fails like Go's "Could not open <file>".
 #pragma once
+#include <charconv>
+#include <cstring>
 #include "scene_ir.hpp"
 #include <map>
 #include <sstream>
@@ -56,12 +58,52 @@ inline std::vector<std::string> fields(const std::string& line) {   // strings.F
     }
     return out;
 }
+// The same split into a vector that is reused from line to line (a 100 MB OBJ has millions of lines: no per-line
+// allocation of the line, the field vector or the fields; tokens of up to 15 characters live in the strings' own buffers).
+inline void fieldsInto(const char* a, const char* b, std::vector<std::string>& out) {
+    auto sp = [](char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\n' || c == '\v' || c == '\f'; };
+    size_t k = 0;
+    while (a < b) {
+        while (a < b && sp(*a)) a++;
+        const char* e = a;
+        while (e < b && !sp(*e)) e++;
+        if (e > a) { if (k < out.size()) out[k].assign(a, (size_t)(e - a)); else out.emplace_back(a, (size_t)(e - a)); k++; }
+        a = e;
+    }
+    out.resize(k);
+}
+// bufio.Scanner over the text: successive lines [a, b) without their '\n' (the last line may lack one)
+struct LineScan {
+    const char* cur;
+    const char* end;
+    explicit LineScan(const std::string& t) : cur(t.data()), end(t.data() + t.size()) {}
+    bool next(const char*& a, const char*& b) {
+        if (cur >= end) return false;
+        a = cur;
+        const char* nl = (const char*)memchr(cur, '\n', (size_t)(end - cur));
+        b = nl ? nl : end;
+        cur = nl ? nl + 1 : end;
+        return true;
+    }
+};
+// strings.TrimSpace on a range
+inline void trimRange(const char*& a, const char*& b) {
+    auto sp = [](char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\n' || c == '\v' || c == '\f'; };
+    while (a < b && sp(*a)) a++;
+    while (b > a && sp(b[-1])) b--;
+}
 inline std::string trim(const std::string& s) {   // strings.TrimSpace
     size_t a = s.find_first_not_of(" \t\r\n\v\f"), b = s.find_last_not_of(" \t\r\n\v\f");
     return a == std::string::npos ? std::string() : s.substr(a, b - a + 1);
 }
 inline bool parseFloat(const std::string& s, double& v) {   // strconv.ParseFloat(s, 64): the whole token must parse
     if (s.empty()) return false;
+    // plain decimal tokens (all of a mesh file) through from_chars: correctly rounded like strtod, several times faster;
+    // whatever it does not take whole (a leading '+', hex floats, "Inf") goes to strtod
+    const char* b = s.data();
+    const char* e = b + s.size();
+    auto r = std::from_chars(b, e, v);
+    if (r.ec == std::errc() && r.ptr == e) return true;
     char* end = nullptr;
     v = std::strtod(s.c_str(), &end);
     return end && *end == 0;
@@ -187,11 +229,12 @@ inline bool loadObj(ir::Scene& sc, const std::string& objText, const std::string
     bool haveLib = false;
     if (!opt.IgnoreMtl && !mtlText.empty()) {
         // the reference only loads the library when the OBJ names one (mtllib), :105-133
-        std::istringstream scan(objText);
-        std::string raw;
+        LineScan scan(objText);
+        const char *la, *lb;
+        std::vector<std::string> p;
         bool named = false;
-        while (std::getline(scan, raw)) {
-            std::vector<std::string> p = fields(trim(raw));
+        while (scan.next(la, lb)) {
+            fieldsInto(la, lb, p);
             if (p.size() >= 2 && p[0] == "mtllib") { named = true; break; }
         }
         if (named) { if (!loadMtl(sc, mtlText, opt, lib, err)) return false; haveLib = true; }
@@ -202,12 +245,13 @@ inline bool loadObj(ir::Scene& sc, const std::string& objText, const std::string
     double mn[3] = {1.7976931348623157e308, 1.7976931348623157e308, 1.7976931348623157e308};
     double mx[3] = {-1.7976931348623157e308, -1.7976931348623157e308, -1.7976931348623157e308};
     {
-        std::istringstream in(objText);
-        std::string raw;
-        while (std::getline(in, raw)) {
-            std::string line = trim(raw);
-            if (line.empty() || line[0] == '#') continue;
-            std::vector<std::string> p = fields(line);
+        LineScan in(objText);
+        const char *la, *lb;
+        std::vector<std::string> p;
+        while (in.next(la, lb)) {
+            trimRange(la, lb);
+            if (la == lb || *la == '#') continue;
+            fieldsInto(la, lb, p);
             if (p.empty()) continue;
             if (p[0] == "vt") {
                 if (p.size() < 3) continue;
@@ -238,12 +282,15 @@ inline bool loadObj(ir::Scene& sc, const std::string& objText, const std::string
     // second pass: normals and faces (:284-470)
     int currentMaterial = opt.DefaultMaterial;
     std::vector<int> triangles;
-    std::istringstream in(objText);
-    std::string raw;
-    while (std::getline(in, raw)) {
-        std::string line = trim(raw);
-        if (line.empty() || line[0] == '#') continue;
-        std::vector<std::string> p = fields(line);
+    LineScan in(objText);
+    const char *la, *lb;
+    std::vector<std::string> p, idx;
+    std::vector<V3> fv, fn;
+    std::vector<std::array<double, 2>> ft;
+    while (in.next(la, lb)) {
+        trimRange(la, lb);
+        if (la == lb || *la == '#') continue;
+        fieldsInto(la, lb, p);
         if (p.empty()) continue;
         if (p[0] == "vn") {
             if (p.size() < 4) continue;
@@ -260,11 +307,21 @@ inline bool loadObj(ir::Scene& sc, const std::string& objText, const std::string
             currentMaterial = it != lib.end() ? it->second.Material : opt.DefaultMaterial;
         } else if (p[0] == "f") {
             if (p.size() < 4) continue;
-            std::vector<V3> fv, fn;
-            std::vector<std::array<double, 2>> ft;
+            fv.clear(); fn.clear(); ft.clear();
             for (size_t i = 1; i < p.size(); i++) {
-                std::vector<std::string> idx;   // strings.Split(parts[i], "/")
-                { size_t a = 0; for (;;) { size_t b = p[i].find('/', a); idx.push_back(p[i].substr(a, b == std::string::npos ? b : b - a)); if (b == std::string::npos) break; a = b + 1; } }
+                // strings.Split(parts[i], "/") into the reused vector
+                {
+                    size_t a = 0, k = 0;
+                    for (;;) {
+                        size_t b = p[i].find('/', a);
+                        size_t len = (b == std::string::npos ? p[i].size() : b) - a;
+                        if (k < idx.size()) idx[k].assign(p[i], a, len); else idx.emplace_back(p[i], a, len);
+                        k++;
+                        if (b == std::string::npos) break;
+                        a = b + 1;
+                    }
+                    idx.resize(k);
+                }
                 if (!idx.empty() && !idx[0].empty()) {
                     int k;
                     if (!parseInt(idx[0], k)) continue;
