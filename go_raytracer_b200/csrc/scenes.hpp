@@ -6,6 +6,7 @@
 // no canonical geometry to match; we use fixed seeds and the
 // reference's draw ORDER.
 #pragma once
+#include <charconv>
 #include "scene_ir.hpp"
 #include "obj_loader.hpp"
 #include <cstdio>
@@ -349,15 +350,21 @@ inline std::string displacedSphereObj(int nseg) {
             double len = std::sqrt(n.x * n.x + n.y * n.y + n.z * n.z);
             if (len < 1e-12 || i == 0 || i == nseg) n = p;
             else if (n.x * p.x + n.y * p.y + n.z * p.z < 0) n = ir::neg(n);
-            snprintf(buf, sizeof(buf), "v %.17g %.17g %.17g\nvn %.17g %.17g %.17g\n", p.x, p.y, p.z, n.x, n.y, n.z);
-            out += buf;
+            // shortest round-trip decimals (std::to_chars): the same doubles as "%.17g" would carry, several times faster
+            char* q = buf;
+            auto num = [&](double x) { q = std::to_chars(q, buf + sizeof(buf), x).ptr; };
+            *q++ = 'v'; *q++ = ' '; num(p.x); *q++ = ' '; num(p.y); *q++ = ' '; num(p.z); *q++ = '\n';
+            *q++ = 'v'; *q++ = 'n'; *q++ = ' '; num(n.x); *q++ = ' '; num(n.y); *q++ = ' '; num(n.z); *q++ = '\n';
+            out.append(buf, (size_t)(q - buf));
         }
     }
     for (int i = 0; i < nseg; i++) {
         for (int j = 0; j < nseg; j++) {
             int a = i * (nseg + 1) + j + 1, b = a + 1, c = a + (nseg + 1), d = c + 1;   // OBJ indices are 1-based
-            snprintf(buf, sizeof(buf), "f %d//%d %d//%d %d//%d %d//%d\n", a, a, b, b, d, d, c, c);
-            out += buf;
+            char* q = buf;
+            auto idx = [&](int k) { q = std::to_chars(q, buf + sizeof(buf), k).ptr; *q++ = '/'; *q++ = '/'; q = std::to_chars(q, buf + sizeof(buf), k).ptr; };
+            *q++ = 'f'; *q++ = ' '; idx(a); *q++ = ' '; idx(b); *q++ = ' '; idx(d); *q++ = ' '; idx(c); *q++ = '\n';
+            out.append(buf, (size_t)(q - buf));
         }
     }
     return out;
