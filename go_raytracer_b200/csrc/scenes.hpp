@@ -352,9 +352,11 @@ inline std::string displacedSphereObj(int nseg) {
             else if (n.x * p.x + n.y * p.y + n.z * p.z < 0) n = ir::neg(n);
             // shortest round-trip decimals (std::to_chars): the same doubles as "%.17g" would carry, several times faster
             char* q = buf;
-            auto num = [&](double x) { q = std::to_chars(q, buf + sizeof(buf), x).ptr; };
-            *q++ = 'v'; *q++ = ' '; num(p.x); *q++ = ' '; num(p.y); *q++ = ' '; num(p.z); *q++ = '\n';
-            *q++ = 'v'; *q++ = 'n'; *q++ = ' '; num(n.x); *q++ = ' '; num(n.y); *q++ = ' '; num(n.z); *q++ = '\n';
+            char* const qe = buf + sizeof(buf) - 1;
+            auto ch = [&](char c) { if (q < qe) *q++ = c; };
+            auto num = [&](double x) { q = std::to_chars(q, qe, x).ptr; };
+            ch('v'); ch(' '); num(p.x); ch(' '); num(p.y); ch(' '); num(p.z); ch('\n');
+            ch('v'); ch('n'); ch(' '); num(n.x); ch(' '); num(n.y); ch(' '); num(n.z); ch('\n');
             out.append(buf, (size_t)(q - buf));
         }
     }
@@ -362,8 +364,10 @@ inline std::string displacedSphereObj(int nseg) {
         for (int j = 0; j < nseg; j++) {
             int a = i * (nseg + 1) + j + 1, b = a + 1, c = a + (nseg + 1), d = c + 1;   // OBJ indices are 1-based
             char* q = buf;
-            auto idx = [&](int k) { q = std::to_chars(q, buf + sizeof(buf), k).ptr; *q++ = '/'; *q++ = '/'; q = std::to_chars(q, buf + sizeof(buf), k).ptr; };
-            *q++ = 'f'; *q++ = ' '; idx(a); *q++ = ' '; idx(b); *q++ = ' '; idx(d); *q++ = ' '; idx(c); *q++ = '\n';
+            char* const qe = buf + sizeof(buf) - 1;
+            auto ch = [&](char c) { if (q < qe) *q++ = c; };
+            auto idx = [&](int k) { q = std::to_chars(q, qe, k).ptr; ch('/'); ch('/'); q = std::to_chars(q, qe, k).ptr; };
+            ch('f'); ch(' '); idx(a); ch(' '); idx(b); ch(' '); idx(d); ch(' '); idx(c); ch('\n');
             out.append(buf, (size_t)(q - buf));
         }
     }
