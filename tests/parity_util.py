@@ -90,3 +90,52 @@ def ref_bvh_order(boxes):
         mid = s + (e - s) // 2
         stack.append((s, mid)); stack.append((mid, e))
     return order
+
+
+def random_scene(seed):
+    """Random instancing / grouping of every flat-able surface type: spheres (static, moving), quads, boxes, triangles,
+    under random Translate / RotateY chains, grouped into lists and BVHs of random size, nested up to three deep."""
+    import numpy as np
+    import go_raytracer_b200 as g
+    rng = np.random.default_rng(seed)
+    sc = g.Scene()
+    mat = sc.NewLambertian((.5, .5, .5))
+
+    def prim():
+        k = rng.integers(0, 5)
+        c = rng.uniform(-8, 8, size=3)
+        if k == 0:
+            return sc.NewSphere(tuple(c), float(rng.uniform(0.2, 1.5)), mat)
+        if k == 1:
+            return sc.NewMotionSphere(tuple(c), tuple(c + rng.uniform(-1, 1, size=3)), float(rng.uniform(0.2, 1.0)), mat)
+        if k == 2:
+            return sc.NewQuad(tuple(c), tuple(rng.uniform(-2, 2, size=3)), tuple(rng.uniform(-2, 2, size=3)), mat)
+        if k == 3:
+            return sc.NewBox(tuple(c), tuple(c + rng.uniform(0.3, 2.0, size=3)), mat)
+        v = [tuple(c + rng.uniform(-1.5, 1.5, size=3)) for _ in range(3)]
+        return sc.NewTriangle(v, mat)
+
+    def instance(obj):
+        for _ in range(rng.integers(0, 3)):
+            if rng.random() < 0.5:
+                obj = sc.Translate(obj, tuple(rng.uniform(-3, 3, size=3)))
+            else:
+                obj = sc.RotateY(obj, float(rng.uniform(-180, 180)))
+        return obj
+
+    def group(depth):
+        n = int(rng.integers(1, 12 if depth else 40))
+        objs = []
+        for _ in range(n):
+            if depth < 2 and rng.random() < 0.15:
+                objs.append(instance(group(depth + 1)))
+            else:
+                objs.append(instance(prim()))
+        lst = sc.NewHittableList(objs)
+        return sc.BuildBVH(lst) if rng.random() < 0.7 else lst
+
+    light = sc.NewQuad((-2, 20, -2), (4, 0, 0), (0, 0, 4), sc.NewDiffuseLight((5, 5, 5)))
+    world = sc.NewHittableList([group(0), light])
+    sc.set_world(world)
+    sc.set_lights(sc.NewHittableList([light]))
+    return sc

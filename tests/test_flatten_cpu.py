@@ -172,3 +172,29 @@ def test_host_camera_matches_oracle_initialize():
             assert getattr(a, f) == getattr(b, f)
         for f in ("center", "pixel00", "delta_u", "delta_v", "defocus_u", "defocus_v", "background"):
             assert np.allclose(list(getattr(a, f)), list(getattr(b, f)), rtol=1e-14, atol=1e-14)
+
+
+@pytest.mark.parametrize("seed", range(6))
+@pytest.mark.parametrize("collapse", [None, (0, 0), (8, 2)])
+def test_random_scenes_flatten_to_the_same_closest_hits(seed, collapse):
+    """The flattener (instance baking, BuildBVH order, leaf runs, box records, hints) against the oracle, which walks
+    the un-flattened description with the reference's transform-at-traversal-time recursion."""
+    sc = PU.random_scene(seed)
+    flat = sc.flatten() if collapse is None else sc.flatten(*collapse)
+    fi = FlatInterp(flat)
+    ow = O.OracleWorld(sc)
+    rng = np.random.default_rng(1000 + seed)
+    n = 500
+    o = rng.uniform(-14, 14, size=(n, 3))
+    tgt = rng.uniform(-6, 6, size=(n, 3))
+    rays = PU.make_rays(o, tgt - o, time=rng.uniform(0, 1, size=n))
+    oh = ow.trace_batch(rays, audit_eps=1e-6)
+    assert (oh["id"] >= 0).mean() > 0.08
+    bad = []
+    for k, (r, h) in enumerate(zip(rays, oh)):
+        if h["flags"]:
+            continue
+        fid, ft = fi.hit(r["o"].astype(np.float64), r["d"].astype(np.float64), float(r["time"]), float(r["tmin"]), float(r["tmax"]))
+        if fid != h["id"] or (fid >= 0 and abs(ft - h["t"]) > 1e-5 * abs(h["t"])):
+            bad.append((k, fid, int(h["id"]), ft, float(h["t"])))
+    assert not bad, bad[:5]

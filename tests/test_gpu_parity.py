@@ -417,3 +417,24 @@ def test_in_process_multi_gpu_matches_single_gpu():
             fin = np.isfinite(one) & np.isfinite(two)
             assert fin.mean() > 0.999
             assert np.allclose(two[fin], one[fin], rtol=1e-4, atol=1e-4), f"scene {sid} p2p={p2p}"
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_scenes_cuda_vs_oracle(seed):
+    """Randomly instanced / grouped scenes of every surface type (tests/parity_util.random_scene): hit ids exact and
+    t to 1e-5 between the CUDA ray query (flattened, baked, fp32) and the oracle (description, transforms at traversal
+    time, fp64), for random rays and for secondary rays with self-exclusion; and the two render variants agree."""
+    sc = PU.random_scene(seed)
+    ow, dev = O.OracleWorld(sc), g.DeviceScene(sc)
+    rng = np.random.default_rng(2000 + seed)
+    n = 20000
+    o = rng.uniform(-14, 14, size=(n, 3))
+    tgt = rng.uniform(-6, 6, size=(n, 3))
+    rays = PU.make_rays(o, tgt - o, time=rng.uniform(0, 1, size=n))
+    oh = ow.trace_batch(rays, audit_eps=1e-5)
+    r = PU.compare_hits(dev.trace_batch(rays), oh, t_rel=T_REL)
+    assert r["id_mismatch_unflagged"] == 0 and r["t_bad"] == 0, (seed, r["bad_id_idx"], r["bad_t_idx"], r["t_max_rel_unflagged"])
+    assert r["hits"] > 0.05 * n and r["flagged"] < 0.05 * n
+    sec = PU.secondary_batch(oh, rng, time=rays["time"])
+    r2 = PU.compare_hits(dev.trace_batch(sec), ow.trace_batch(sec, audit_eps=1e-5, use_exclusion=True), t_rel=T_REL)
+    assert r2["id_mismatch_unflagged"] == 0 and r2["t_bad"] == 0, (seed, r2["bad_id_idx"], r2["bad_t_idx"])
