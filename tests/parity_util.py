@@ -139,3 +139,65 @@ def random_scene(seed):
     sc.set_world(world)
     sc.set_lights(sc.NewHittableList([light]))
     return sc
+
+
+def random_shaded_scene(seed):
+    """random_scene's geometry with every material class (Lambertian with solid / checker / noise textures, metal,
+    dielectric, isotropic) and one or two constant media whose boundaries are instanced spheres or boxes."""
+    import numpy as np
+    import go_raytracer_b200 as g
+    rng = np.random.default_rng(5000 + seed)
+    sc = g.Scene()
+
+    def material():
+        k = rng.integers(0, 6)
+        c = tuple(rng.uniform(0.2, 0.9, size=3))
+        if k == 0:
+            return sc.NewLambertian(c)
+        if k == 1:
+            return sc.NewTexturedLambertian(sc.NewCheckerboardColors(float(rng.uniform(0.3, 2.0)), c, (0.9, 0.9, 0.9)))
+        if k == 2:
+            return sc.NewTexturedLambertian(sc.NewNoiseTextureWithType(float(rng.uniform(0.5, 4.0)), int(rng.integers(1, 4)), int(seed + 1)))
+        if k == 3:
+            return sc.NewMetal(c, float(rng.uniform(0.0, 0.6)))
+        if k == 4:
+            return sc.NewDielectric(float(rng.uniform(1.2, 1.8)))
+        return sc.NewLambertian(c)
+
+    def instance(obj):
+        for _ in range(rng.integers(0, 3)):
+            obj = sc.Translate(obj, tuple(rng.uniform(-2, 2, size=3))) if rng.random() < 0.5 else sc.RotateY(obj, float(rng.uniform(-180, 180)))
+        return obj
+
+    objs = [sc.NewQuad((-12, -3, -12), (24, 0, 0), (0, 0, 24), sc.NewLambertian((.6, .6, .6)))]      # a floor
+    for _ in range(int(rng.integers(12, 70))):     # below ~32 leaves the flattener emits one run, above it a BVH
+        c = rng.uniform(-6, 6, size=3)
+        k = rng.integers(0, 4)
+        m = material()
+        if k == 0:
+            o = sc.NewSphere(tuple(c), float(rng.uniform(0.4, 1.6)), m)
+        elif k == 1:
+            o = sc.NewBox(tuple(c), tuple(c + rng.uniform(0.5, 2.0, size=3)), m)
+        elif k == 2:
+            o = sc.NewQuad(tuple(c), tuple(rng.uniform(-2, 2, size=3)), tuple(rng.uniform(-2, 2, size=3)), m)
+        else:
+            o = sc.NewTriangle([tuple(c + rng.uniform(-1.5, 1.5, size=3)) for _ in range(3)], m)
+        objs.append(instance(o))
+    for _ in range(int(rng.integers(1, 3))):
+        c = rng.uniform(-5, 5, size=3)
+        white = sc.NewLambertian((1, 1, 1))
+        if rng.random() < 0.5:
+            b = sc.NewSphere(tuple(c), float(rng.uniform(1.0, 2.5)), white)
+        else:
+            b = sc.NewBox(tuple(c), tuple(c + rng.uniform(1.0, 3.0, size=3)), white)
+        objs.append(sc.ConstantMedium(instance(b), float(rng.uniform(0.05, 0.6)), tuple(rng.uniform(0.1, 0.9, size=3))))
+    light = sc.NewQuad((-3, 9, -3), (6, 0, 0), (0, 0, 6), sc.NewDiffuseLight((6, 6, 6)))
+    objs.append(light)
+    lst = sc.NewHittableList(objs)
+    sc.set_world(sc.BuildBVH(lst) if seed % 2 == 1 else lst)      # odd seeds: a BVH over everything, media included
+    sc.set_lights(sc.NewHittableList([light]))
+    cam = g.Camera()
+    cam.AspectRatio, cam.Width, cam.SamplesPerPixel, cam.MaxDepth = 1.0, 40, 16, 20
+    cam.VerticalFOV, cam.Background = 50.0, (0.3, 0.4, 0.6)
+    cam.PositionCamera((0, 3, -16), (0, 0, 0), (0, 1, 0))
+    return sc, cam.config()
