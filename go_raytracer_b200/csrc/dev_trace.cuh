@@ -119,6 +119,9 @@ __device__ __forceinline__ SceneView make_view(const DevScene& ds, unsigned char
 struct RayD {
     f3 o, d, invd;
     float time;
+    // float4 index, inside a 4-wide node, of the NEAR x / y / z planes of its four children (0/3, 1/4, 2/5 by the sign
+    // of 1/d; the far planes are 3 - nx, 5 - ny, 7 - nz): the slab test needs no per-axis min/max or swap (aabb.go:102-104)
+    uint32_t nx, ny, nz;
     // fp64 copies for the cancellation-prone sums (sphere quadratic, rotated-quad planes)
     d3 o64, d64;
     double a64;  // d.d
@@ -126,7 +129,10 @@ struct RayD {
 template <uint32_t FEAT>
 __device__ __forceinline__ void ray_setup(RayD& r, f3 o, f3 d, float time) {
     r.o = o; r.d = d; r.time = time;
-    if (FEAT & F_NODE) r.invd = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);  // aabb.go:96 (only box tests use it)
+    if (FEAT & F_NODE) {
+        r.invd = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);  // aabb.go:96 (only box tests use it)
+        r.nx = r.invd.x < 0.0f ? 3u : 0u; r.ny = r.invd.y < 0.0f ? 4u : 1u; r.nz = r.invd.z < 0.0f ? 5u : 2u;
+    }
     if (GRT_NEEDS_F64(FEAT)) {
         r.o64 = tod3(o); r.d64 = tod3(d);
         r.a64 = dot(r.d64, r.d64);
@@ -160,19 +166,23 @@ __device__ __forceinline__ bool box_hit(float lx, float ly, float lz, float hx, 
     return !(hi <= lo);
 }
 
-// Device BVH node, 64 bytes, built at upload from the ABI's GrtNode array: a node carries the boxes of its TWO
-// children, so one visit is one 64-byte fetch and two independent slab tests, and the dependent chain per tree level
-// is one load instead of two.  A child that is not an inner node (a primitive, list or medium: the reference does
-// not box-test those, bvh.go:73-79) gets the infinite box, i.e. it is always visited while tmax > tmin.
-//   q0 = l.min.xyz, l.max.x   q1 = l.max.yz, r.min.xy   q2 = r.min.z, r.max.xyz   q3 = left, right (bit 31: order hint), 0, 0
-#define GRT_DNODE_F4 4
+// Device BVH node: 4-wide, 128 bytes (8 x float4), built at upload from the ABI's binary GrtNode array (wide_bvh.hpp):
+//   f4[0..2] = lo.x, lo.y, lo.z of the four children   f4[3..5] = hi.x, hi.y, hi.z
+//   f4[6]    = the four child refs (inner node, DREF_RUN primitive run, list, medium; NONE = empty slot, empty box)
+//   f4[7].x  = bit 0: children may be visited nearest first (no constantMedium below), .y = number of children
+// Every child carries its own box — leaf runs too, which the reference does not box-test (bvh.go:73-79); a
+// conservative box cannot change a closest hit, it only saves fetching primitives the ray passes by.
+#define GRT_WNODE_F4 8
+// child ref of a run of consecutive primitives: bit 31 | type << 28 | (count - 1) << 25 | first index (wide_bvh.hpp)
+#define GRT_DREF_RUN_BIT 0x80000000u
+#define GRT_DREF_RUN_INDEX_MASK 0x01FFFFFFu
 
 // ---- sphere.Hit, objects.go:83-115 ----------------------------------------
 // The cancellation-prone sums (c = |oc|^2 - r^2, disc = h^2 - a c) are fp64;
 // the roots use the cancellation-free pair {c/q, q/a}, q = h + sign(h) sqrt(disc),
 // which equals {(h-s)/a, (h+s)/a} of the reference up to rounding.
 // `self`: the ray origin lies on this sphere; exact arithmetic has c == 0.
-__device__ __forceinline__ bool sphere_hit(const GrtSphere& s, const RayD& r, float tmin, float tmax, bool self, float& t_out) {
+__device__ __forceinline__ bool sphere_roots(const GrtSphere& s, const RayD& r, bool self, float& nearr, float& farr) {
     double cx = s.c0[0] + (double)r.time * (double)s.dc[0];
     double cy = s.c0[1] + (double)r.time * (double)s.dc[1];
     double cz = s.c0[2] + (double)r.time * (double)s.dc[2];
@@ -184,16 +194,24 @@ __device__ __forceinline__ bool sphere_hit(const GrtSphere& s, const RayD& r, fl
     if (disc < 0) return false;
     float hf = (float)h, af = (float)r.a64, cf = (float)c;
     float sq = sqrtf((float)disc);
-    float nearr, farr;
     if (hf >= 0) { float q = hf + sq; farr = q / af; nearr = cf / q; }
     else { float q = hf - sq; nearr = q / af; farr = cf / q; }
+    return true;
+}
+// Surrounds: open interval, nearer root first (objects.go:101-105)
+__device__ __forceinline__ bool sphere_pick(float nearr, float farr, float tmin, float tmax, float& t_out) {
     float root = nearr;
-    if (!(tmin < root && root < tmax)) {   // Surrounds: open interval (objects.go:101-105)
+    if (!(tmin < root && root < tmax)) {
         root = farr;
         if (!(tmin < root && root < tmax)) return false;
     }
     t_out = root;
     return true;
+}
+__device__ __forceinline__ bool sphere_hit(const GrtSphere& s, const RayD& r, float tmin, float tmax, bool self, float& t_out) {
+    float nearr, farr;
+    if (!sphere_roots(s, r, self, nearr, farr)) return false;
+    return sphere_pick(nearr, farr, tmin, tmax, t_out);
 }
 
 // One MUFU.RCP (1 ulp) and a multiply; __fdividef adds ~5 range-scaling instructions we do not need
@@ -260,7 +278,8 @@ __device__ __forceinline__ float quad_refine_t(const DQuadCold* q, const RayD& r
 // Returns the face index in NewBox's order (front, right, back, left, top, bottom) or -1.
 // `excl_face`: face of THIS box the ray starts on (-1 if none).  `near_tmin` reports a candidate
 // within fp32 resolution of tmin (see F_TMIN_F64).
-__device__ __forceinline__ int box_prim_hit(const GrtBox* bx, const RayD& r, float tmin, float tmax, int excl_face, float& t_out, bool& near_tmin) {
+struct BoxSlab { float t_enter, t_exit, d_enter, d_exit; int f_enter, f_exit; };
+__device__ __forceinline__ bool box_prim_slab(const GrtBox* bx, const RayD& r, BoxSlab& o) {
     const float4 b0 = *(const float4*)&bx->mn[0], b1 = *(const float4*)&bx->mx[0], b2 = *(const float4*)&bx->T[0];
     const float rs = bx->rs, rc = b2.w;
     const float px = r.o.x - b2.x, py = r.o.y - b2.y, pz = r.o.z - b2.z;
@@ -276,23 +295,32 @@ __device__ __forceinline__ int box_prim_hit(const GrtBox* bx, const RayD& r, flo
     const float lox = fminf(ax, bx_), hix = fmaxf(ax, bx_);
     const float loy = fminf(ay, by), hiy = fmaxf(ay, by);
     const float loz = fminf(az, bz), hiz = fmaxf(az, bz);
-    const float t_enter = fmaxf(fmaxf(lox, loy), loz), t_exit = fminf(fminf(hix, hiy), hiz);
-    near_tmin = false;
-    if (!(t_enter <= t_exit)) return -1;
+    o.t_enter = fmaxf(fmaxf(lox, loy), loz); o.t_exit = fminf(fminf(hix, hiy), hiz);
+    if (!(o.t_enter <= o.t_exit)) return false;
     // faces: 0 front z=max, 1 right x=max, 2 back z=min, 3 left x=min, 4 top y=max, 5 bottom y=min
     // entering through axis a: the min face when d_a > 0, else the max face; leaving: the other way round
     // (selects, no branches: the three axes are equally likely and would split the warp three ways)
     const int fx_in = dx > 0 ? 3 : 1, fy_in = dy > 0 ? 5 : 4, fz_in = dz > 0 ? 2 : 0;
     const bool ex = (lox >= loy) & (lox >= loz), ey = loy >= loz;
-    const int f_enter = ex ? fx_in : (ey ? fy_in : fz_in);
-    const float d_enter = ex ? dx : (ey ? dy : dz);
+    o.f_enter = ex ? fx_in : (ey ? fy_in : fz_in);
+    o.d_enter = ex ? dx : (ey ? dy : dz);
     const bool xx = (hix <= hiy) & (hix <= hiz), xy = hiy <= hiz;
-    const int f_exit = xx ? (4 - fx_in) : (xy ? (9 - fy_in) : (2 - fz_in));   // the opposite face of the same axis
-    const float d_exit = xx ? dx : (xy ? dy : dz);
-    near_tmin = (fabsf((t_enter - tmin) * d_enter) < 2.5e-4f) | (fabsf((t_exit - tmin) * d_exit) < 2.5e-4f);
-    if (tmin <= t_enter && t_enter <= tmax && f_enter != excl_face) { t_out = t_enter; return f_enter; }
-    if (tmin <= t_exit && t_exit <= tmax && f_exit != excl_face) { t_out = t_exit; return f_exit; }
+    o.f_exit = xx ? (4 - fx_in) : (xy ? (9 - fy_in) : (2 - fz_in));   // the opposite face of the same axis
+    o.d_exit = xx ? dx : (xy ? dy : dz);
+    return true;
+}
+// the smaller of (t_enter, t_exit) that lies in [tmin, tmax] (closed, objects.go:177) and is not on the excluded face
+__device__ __forceinline__ int box_prim_pick(const BoxSlab& o, float tmin, float tmax, int excl_face, float& t_out, bool& near_tmin) {
+    near_tmin = (fabsf((o.t_enter - tmin) * o.d_enter) < 2.5e-4f) | (fabsf((o.t_exit - tmin) * o.d_exit) < 2.5e-4f);
+    if (tmin <= o.t_enter && o.t_enter <= tmax && o.f_enter != excl_face) { t_out = o.t_enter; return o.f_enter; }
+    if (tmin <= o.t_exit && o.t_exit <= tmax && o.f_exit != excl_face) { t_out = o.t_exit; return o.f_exit; }
     return -1;
+}
+__device__ __forceinline__ int box_prim_hit(const GrtBox* bx, const RayD& r, float tmin, float tmax, int excl_face, float& t_out, bool& near_tmin) {
+    BoxSlab o;
+    near_tmin = false;
+    if (!box_prim_slab(bx, r, o)) return -1;
+    return box_prim_pick(o, tmin, tmax, excl_face, t_out, near_tmin);
 }
 
 // ---- Triangle.Hit (Möller–Trumbore), objects.go:408-461 --------------------
@@ -465,6 +493,10 @@ __device__ __forceinline__ bool trav_run(const SceneView& sv, TS& ts, const RayD
 
     // one item that is not an inner node: a list (scanned in order), a medium, or a primitive
     auto leaf = [&](uint32_t ref) {
+        if ((FEAT & F_NODE) && (ref & GRT_DREF_RUN_BIT)) {   // a leaf run named by its parent node: (type, count, first index)
+            test_prims((ref & (7u << GRT_REF_SHIFT)) | (ref & GRT_DREF_RUN_INDEX_MASK), ((ref >> 25) & 7u) + 1u);
+            return;
+        }
         uint32_t type = GRT_REF_TYPE(ref);
         uint32_t idx = ref & GRT_REF_MASK;
         if ((FEAT & F_LIST) && type == GRT_REF_LIST) {
@@ -492,8 +524,27 @@ __device__ __forceinline__ bool trav_run(const SceneView& sv, TS& ts, const RayD
             if (STATS) tc->medium++;
             HitInfo h1, h2;
             const float INF = __int_as_float(0x7f800000);
-            if (!closest_hit<FEAT, true, STATS>(sv, m.boundary, r, -INF, INF, GRT_NO_ID, 0xFFFFFFFFu, nullptr, h1, tc)) return;
-            if (!closest_hit<FEAT, true, STATS>(sv, m.boundary, r, h1.t + 0.0001f, INF, GRT_NO_ID, 0xFFFFFFFFu, nullptr, h2, tc)) return;
+            // the two boundary queries of medium.go:32-37: (-inf, inf), then (t1 + 0.0001, inf).  When the boundary is a
+            // single sphere or NewBox (every medium of main.go) both answers come from ONE solve — the same floats the two
+            // general queries would return, without two nested traversals
+            const uint32_t btype = GRT_REF_TYPE(m.boundary), bidx = m.boundary & GRT_REF_MASK;
+            if ((FEAT & F_SPHERE) && btype == GRT_REF_SPHERE) {
+                if (STATS) tc->sphere += 2;
+                float nearr, farr;
+                if (!sphere_roots(sv.spheres()[bidx], r, false, nearr, farr)) return;
+                if (!sphere_pick(nearr, farr, -INF, INF, h1.t)) return;
+                if (!sphere_pick(nearr, farr, h1.t + 0.0001f, INF, h2.t)) return;
+            } else if ((FEAT & F_BOX) && !(FEAT & F_TMIN_F64) && btype == GRT_REF_BOX) {
+                if (STATS) tc->box += 2;
+                BoxSlab bs;
+                bool nt;
+                if (!box_prim_slab(sv.boxes() + bidx, r, bs)) return;
+                if (box_prim_pick(bs, -INF, INF, -1, h1.t, nt) < 0) return;
+                if (box_prim_pick(bs, h1.t + 0.0001f, INF, -1, h2.t, nt) < 0) return;
+            } else {
+                if (!closest_hit<FEAT, true, STATS>(sv, m.boundary, r, -INF, INF, GRT_NO_ID, 0xFFFFFFFFu, nullptr, h1, tc)) return;
+                if (!closest_hit<FEAT, true, STATS>(sv, m.boundary, r, h1.t + 0.0001f, INF, GRT_NO_ID, 0xFFFFFFFFu, nullptr, h2, tc)) return;
+            }
             float t1 = fmaxf(h1.t, tmin), t2 = fminf(h2.t, tmax);
             if (t1 >= t2) return;
             t1 = fmaxf(0.0f, t1);
@@ -509,27 +560,41 @@ __device__ __forceinline__ bool trav_run(const SceneView& sv, TS& ts, const RayD
         }
         test_prims(ref, 1);   // a primitive that is a direct BVH child (bvh.go:73,79), or NONE
     };
-    // one inner node: box test, then the near/left child becomes current and the other waits on the stack
+    // one inner node: four slab tests, then the nearest hit child (or, under a medium, the first in the reference's
+    // order) becomes current and the other hit children wait on the stack, nearest on top
     auto node_step = [&](uint32_t& ref) -> bool {   // false: the stack ran dry
-        const uint32_t ni = ref & GRT_REF_MASK;
-        const float4 q0 = nodes[GRT_DNODE_F4 * ni], q1 = nodes[GRT_DNODE_F4 * ni + 1], q2 = nodes[GRT_DNODE_F4 * ni + 2];
-        const uint2 ch = *(const uint2*)(nodes + GRT_DNODE_F4 * ni + 3);
-        if (STATS) tc->box += 2;
-        bool hl = box_hit(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, r, tmin, tmax);
-        bool hr = box_hit(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, r, tmin, tmax);
-        uint32_t l = ch.x, rr = ch.y;
-        const uint32_t hint = (l >> 31) | ((rr >> 31) << 1);   // 0: reference order; 1..3: split axis + 1
-        l &= ~GRT_NODE_HINT_BIT; rr &= ~GRT_NODE_HINT_BIT;
-        if (hint) {
-            const float da = hint == 1u ? r.d.x : (hint == 2u ? r.d.y : r.d.z);
-            if (da < 0.0f) { const uint32_t tmp = l; l = rr; rr = tmp; const bool tb = hl; hl = hr; hr = tb; }   // the far child waits on the stack
-        }
-        if (hl) {
-            if (hr) ts.at(sp++) = rr;
-            ref = l;
+        const float4* np = nodes + GRT_WNODE_F4 * (ref & GRT_REF_MASK);
+        const float4 pnx = np[r.nx], pny = np[r.ny], pnz = np[r.nz];
+        const float4 pfx = np[3u - r.nx], pfy = np[5u - r.ny], pfz = np[7u - r.nz];
+        const uint4 ch = *(const uint4*)(np + 6);
+        const uint2 meta = *(const uint2*)(np + 7);
+        if (STATS) tc->box += meta.y;
+        const float INF = __int_as_float(0x7f800000);
+        const bool ordered = (meta.x & 1u) != 0u;
+        // aabb.go:94-110 per child: t = (plane - origin) * (1/d), shrink [tmin, tmax], reject when max < min.
+        // The test must be CONSERVATIVE in fp32 (a box may only be rejected if fp64 rejects it too): a leaf box around a
+        // planar primitive is ~1e-4 thin, and seen from 1000 units away its two planes round to the same t.  Every t
+        // carries a relative error <= 1.5 * 2^-23 (1/d and the product each round once; plane - origin is exact to half
+        // an ulp of the result and monotonic), so the far side is widened by 4 * 2^-23 and equality counts as a hit.
+#define GRT_SLAB(K, C)                                                                                                          \
+        const float tn##K = fmaxf(fmaxf((pnx.C - r.o.x) * r.invd.x, (pny.C - r.o.y) * r.invd.y), fmaxf((pnz.C - r.o.z) * r.invd.z, tmin)); \
+        const float tf##K = fminf(fminf(fminf((pfx.C - r.o.x) * r.invd.x, (pfy.C - r.o.y) * r.invd.y), (pfz.C - r.o.z) * r.invd.z) * 1.00000048f, tmax); \
+        float k##K = (tn##K <= tf##K) ? (ordered ? tn##K : (float)K) : INF;
+        GRT_SLAB(0, x) GRT_SLAB(1, y) GRT_SLAB(2, z) GRT_SLAB(3, w)
+#undef GRT_SLAB
+        uint32_t c0 = ch.x, c1 = ch.y, c2 = ch.z, c3 = ch.w;
+        // sorting network on (key, ref): misses (key = inf) sink to the end
+#define GRT_CSWAP(A, B) { const bool sw_ = k##B < k##A; const float lo_ = fminf(k##A, k##B), hi_ = fmaxf(k##A, k##B); \
+                          const uint32_t ca_ = sw_ ? c##B : c##A, cb_ = sw_ ? c##A : c##B; k##A = lo_; k##B = hi_; c##A = ca_; c##B = cb_; }
+        GRT_CSWAP(0, 1) GRT_CSWAP(2, 3) GRT_CSWAP(0, 2) GRT_CSWAP(1, 3) GRT_CSWAP(1, 2)
+#undef GRT_CSWAP
+        if (k0 < INF) {
+            if (k3 < INF) ts.at(sp++) = c3;
+            if (k2 < INF) ts.at(sp++) = c2;
+            if (k1 < INF) ts.at(sp++) = c1;
+            ref = c0;
             return true;
         }
-        if (hr) { ref = rr; return true; }
         if (sp == 0) { ref = GRT_MAKE_REF(GRT_REF_NONE, 0); return false; }
         ref = ts.at(--sp);
         return true;

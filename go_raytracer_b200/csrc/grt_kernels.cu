@@ -23,6 +23,7 @@
 
 #include "dev_shade.cuh"
 #include "grt_internal.h"
+#include "wide_bvh.hpp"
 
 using namespace grtd;
 
@@ -501,28 +502,18 @@ static int need_device(int device) {
     return GRT_OK;
 }
 
-extern "C" int grt_scene_upload(const GrtScene* s, int device, GrtSceneHandle* out) {
-    if (!out) { grt_set_error("out handle is NULL"); return GRT_E_INVALID; }
-    *out = nullptr;
-    int rc = validate_scene(s);
-    if (rc) return rc;
-    rc = need_device(device);
-    if (rc) return rc;
-    CUDA_TRY(cudaSetDevice(device));
-    GrtSceneDev* h = new GrtSceneDev();
-    h->device = device;
-    DevScene& ds = h->ds;
-    memset(&ds, 0, sizeof(ds));
-    // ---- pack the blob ------------------------------------------------------
-    uint32_t off = 0;
-    auto place = [&](uint32_t bytes) { uint32_t o = off; off = align16(off + bytes); return o; };
-    ds.off_nodes = place(s->n_nodes * (uint32_t)(GRT_DNODE_F4 * 16));
-    ds.off_spheres = place(s->n_spheres * (uint32_t)sizeof(GrtSphere));
-    ds.off_quads = place(s->n_quads * (uint32_t)sizeof(DQuadHot));
-    // run-length list entries (device-internal): consecutive items of one primitive type with
+// ---- device-internal repacking (host side of the upload; also reachable without a device, for the CPU tests) ------
+struct Repacked {
+    std::vector<uint32_t> entries;     // run-length list entries, pairs {first ref | LAST, count}
+    std::vector<GrtMedium> media;      // boundary refs remapped
+    grt::wide::Result wide;            // the 4-wide BVH
+    uint32_t root = 0, n_entries = 0;
+};
+static int repack_scene(const GrtScene* s, Repacked& R) {
+    // run-length list entries: consecutive items of one primitive type with
     // consecutive indices collapse into {first ref, count}; LIST refs are remapped to entry indices
     std::vector<uint32_t> item2entry(s->n_items + 1, 0);
-    std::vector<uint32_t> entries;   // pairs
+    std::vector<uint32_t>& entries = R.entries;
     for (uint32_t i = 0; i < s->n_items;) {
         uint32_t ref = s->items[i] & ~GRT_LIST_LAST;
         uint32_t t = GRT_REF_TYPE(ref);
@@ -549,9 +540,74 @@ extern "C" int grt_scene_upload(const GrtScene* s, int device, GrtSceneHandle* o
     for (size_t k = 0; k < entries.size(); k += 2) entries[k] = remap(entries[k]);
     std::vector<GrtNode> nodes(s->nodes, s->nodes + s->n_nodes);
     for (auto& n : nodes) { n.left = remap(n.left); n.right = remap(n.right); }
-    std::vector<GrtMedium> media(s->media, s->media + s->n_media);
-    for (auto& m : media) m.boundary = remap(m.boundary);
-    const uint32_t n_entries = (uint32_t)(entries.size() / 2);
+    R.media.assign(s->media, s->media + s->n_media);
+    for (auto& m : R.media) m.boundary = remap(m.boundary);
+    R.n_entries = (uint32_t)(entries.size() / 2);
+    // the 4-wide BVH (wide_bvh.hpp): NODE refs held by lists, media and the root now index the wide array
+    grt::wide::Builder wb(s, nodes, entries, R.media);
+    if (!wb.run(remap(s->root), R.wide)) { grt_set_error("wide BVH build: " + R.wide.error); return GRT_E_UNSUPPORTED; }
+    if (R.wide.need_main > GRT_STACK_MAIN || R.wide.need_boundary > GRT_STACK_BOUNDARY) {
+        grt_set_error("scene needs a deeper traversal stack than the kernels provide");
+        return GRT_E_UNSUPPORTED;
+    }
+    auto to_wide = [&](uint32_t ref) -> uint32_t {
+        uint32_t flag = ref & GRT_LIST_LAST, r = ref & ~GRT_LIST_LAST;
+        if (GRT_REF_TYPE(r) == GRT_REF_NODE) r = GRT_MAKE_REF(GRT_REF_NODE, R.wide.node_map[r & GRT_REF_MASK]);
+        return r | flag;
+    };
+    for (size_t k = 0; k < entries.size(); k += 2) entries[k] = to_wide(entries[k]);
+    for (auto& m : R.media) m.boundary = to_wide(m.boundary);
+    R.root = to_wide(remap(s->root));
+    return GRT_OK;
+}
+
+// Test hook (no device needed): the wide BVH and run-length entries the upload would build for this scene.
+// wnodes: capacity cap_nodes x 32 floats; entries: capacity cap_entries x 2 words.  Returns GRT_E_INVALID when too small.
+extern "C" int grt_debug_repack(const GrtScene* s, float* wnodes, uint32_t cap_nodes, uint32_t* n_wide, uint32_t* entries, uint32_t cap_entries,
+                                uint32_t* n_entries, uint32_t* root, uint32_t* media_boundaries, int* need_main, int* need_boundary) {
+    int rc = validate_scene(s);
+    if (rc) return rc;
+    Repacked R;
+    if ((rc = repack_scene(s, R))) return rc;
+    if (n_wide) *n_wide = R.wide.n_wide;
+    if (n_entries) *n_entries = R.n_entries;
+    if (root) *root = R.root;
+    if (need_main) *need_main = R.wide.need_main;
+    if (need_boundary) *need_boundary = R.wide.need_boundary;
+    if (R.wide.n_wide > cap_nodes || R.n_entries > cap_entries) { grt_set_error("grt_debug_repack: output buffers too small"); return GRT_E_INVALID; }
+    if (wnodes) memcpy(wnodes, R.wide.wnodes.data(), (size_t)R.wide.n_wide * GRT_WNODE_FLOATS * sizeof(float));
+    if (entries) memcpy(entries, R.entries.data(), (size_t)R.n_entries * 8);
+    if (media_boundaries) for (size_t i = 0; i < R.media.size(); i++) media_boundaries[i] = R.media[i].boundary;
+    return GRT_OK;
+}
+
+extern "C" int grt_scene_upload(const GrtScene* s, int device, GrtSceneHandle* out) {
+    if (!out) { grt_set_error("out handle is NULL"); return GRT_E_INVALID; }
+    *out = nullptr;
+    int rc = validate_scene(s);
+    if (rc) return rc;
+    rc = need_device(device);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(device));
+    GrtSceneDev* h = new GrtSceneDev();
+    struct Guard { GrtSceneDev* h; ~Guard() { if (h) grt_scene_free(h); } } guard{h};   // every early return frees the handle
+    h->device = device;
+    DevScene& ds = h->ds;
+    memset(&ds, 0, sizeof(ds));
+    // ---- device-internal repacking (list entries, 4-wide BVH) --------------------
+    Repacked RP;
+    if ((rc = repack_scene(s, RP))) return rc;
+    std::vector<uint32_t>& entries = RP.entries;
+    std::vector<GrtMedium>& media = RP.media;
+    grt::wide::Result& wide = RP.wide;
+    const uint32_t n_entries = RP.n_entries;
+    ds.root = RP.root;
+    // ---- pack the blob ------------------------------------------------------
+    uint32_t off = 0;
+    auto place = [&](uint32_t bytes) { uint32_t o = off; off = align16(off + bytes); return o; };
+    ds.off_nodes = place(wide.n_wide * (uint32_t)(GRT_WNODE_F4 * 16));   // offset 0: 128-byte aligned like the allocation
+    ds.off_spheres = place(s->n_spheres * (uint32_t)sizeof(GrtSphere));
+    ds.off_quads = place(s->n_quads * (uint32_t)sizeof(DQuadHot));
     ds.off_boxes = place(s->n_boxes * (uint32_t)sizeof(GrtBox));
     ds.off_items = place(n_entries * 8u);
     ds.off_media = place(s->n_media * (uint32_t)sizeof(GrtMedium));
@@ -565,29 +621,7 @@ extern "C" int grt_scene_upload(const GrtScene* s, int device, GrtSceneHandle* o
     if (off == 0) off = 16;
     std::vector<unsigned char> blob(off, 0);
     auto put = [&](uint32_t o, const void* p, size_t bytes) { if (bytes) memcpy(blob.data() + o, p, bytes); };
-    {   // 64-byte device nodes: the boxes of both children (dev_trace.cuh)
-        std::vector<float> dn((size_t)s->n_nodes * GRT_DNODE_F4 * 4, 0.0f);
-        const float INF = std::numeric_limits<float>::infinity();
-        auto child_box = [&](uint32_t ref, float* lo, float* hi) {
-            ref &= ~GRT_NODE_HINT_BIT;
-            if (GRT_REF_TYPE(ref) == GRT_REF_NODE) {
-                const GrtNode& c = nodes[ref & GRT_REF_MASK];
-                for (int a = 0; a < 3; a++) { lo[a] = c.bmin[a]; hi[a] = c.bmax[a]; }
-            } else {
-                for (int a = 0; a < 3; a++) { lo[a] = -INF; hi[a] = INF; }
-            }
-        };
-        for (uint32_t i = 0; i < s->n_nodes; i++) {
-            float llo[3], lhi[3], rlo[3], rhi[3];
-            child_box(nodes[i].left, llo, lhi);
-            child_box(nodes[i].right, rlo, rhi);
-            float* d = dn.data() + (size_t)i * GRT_DNODE_F4 * 4;
-            d[0] = llo[0]; d[1] = llo[1]; d[2] = llo[2]; d[3] = lhi[0]; d[4] = lhi[1]; d[5] = lhi[2];
-            d[6] = rlo[0]; d[7] = rlo[1]; d[8] = rlo[2]; d[9] = rhi[0]; d[10] = rhi[1]; d[11] = rhi[2];
-            memcpy(d + 12, &nodes[i].left, 4); memcpy(d + 13, &nodes[i].right, 4);
-        }
-        put(ds.off_nodes, dn.data(), dn.size() * sizeof(float));
-    }
+    put(ds.off_nodes, wide.wnodes.data(), (size_t)wide.n_wide * GRT_WNODE_F4 * 16);
     put(ds.off_spheres, s->spheres, s->n_spheres * sizeof(GrtSphere));
     {
         std::vector<DQuadHot> hot(s->n_quads);
@@ -642,10 +676,10 @@ extern "C" int grt_scene_upload(const GrtScene* s, int device, GrtSceneHandle* o
     put(ds.off_images, s->images, s->n_images * sizeof(GrtImage));
     ds.blob_bytes = off;
     ds.stage_bytes = off <= GRT_STAGE_MAX_BYTES ? off : (hot_end <= GRT_STAGE_MAX_BYTES ? hot_end : 0u);
-    ds.n_nodes = s->n_nodes; ds.n_spheres = s->n_spheres; ds.n_quads = s->n_quads; ds.n_boxes = s->n_boxes; ds.n_items = n_entries; ds.n_media = s->n_media;
+    ds.n_nodes = wide.n_wide; ds.n_spheres = s->n_spheres; ds.n_quads = s->n_quads; ds.n_boxes = s->n_boxes; ds.n_items = n_entries; ds.n_media = s->n_media;
     ds.n_materials = s->n_materials; ds.n_textures = s->n_textures; ds.n_lights = s->n_lights; ds.n_images = s->n_images;
     ds.n_tris = s->n_tris; ds.n_perlins = s->n_perlins;
-    ds.root = remap(s->root); ds.lights_mode = s->lights_mode; ds.stack_need = s->max_depth_hint;
+    ds.lights_mode = s->lights_mode; ds.stack_need = (uint32_t)wide.need_main;
     ds.features = scan_features(s);
     auto upload = [&](void** dptr, const void* src, size_t bytes) -> int {
         *dptr = nullptr;
@@ -654,12 +688,12 @@ extern "C" int grt_scene_upload(const GrtScene* s, int device, GrtSceneHandle* o
         CUDA_TRY(cudaMemcpy(*dptr, src, bytes, cudaMemcpyHostToDevice));
         return GRT_OK;
     };
-    if ((rc = upload(&h->d_blob, blob.data(), blob.size()))) { grt_scene_free(h); return rc; }
-    if ((rc = upload(&h->d_tris, s->tris, (size_t)s->n_tris * sizeof(GrtTri)))) { grt_scene_free(h); return rc; }
-    if (s->tri_shade && (rc = upload(&h->d_tri_shade, s->tri_shade, (size_t)s->n_tris * sizeof(GrtTriShade)))) { grt_scene_free(h); return rc; }
-    if (s->tri_v64 && (rc = upload(&h->d_tri_v64, s->tri_v64, (size_t)s->n_tris * 9 * sizeof(double)))) { grt_scene_free(h); return rc; }
-    if ((rc = upload(&h->d_texels, s->texels, (size_t)s->n_texel_bytes))) { grt_scene_free(h); return rc; }
-    if ((rc = upload(&h->d_perlins, s->perlins, (size_t)s->n_perlins * sizeof(GrtPerlin)))) { grt_scene_free(h); return rc; }
+    if ((rc = upload(&h->d_blob, blob.data(), blob.size()))) return rc;
+    if ((rc = upload(&h->d_tris, s->tris, (size_t)s->n_tris * sizeof(GrtTri)))) return rc;
+    if (s->tri_shade && (rc = upload(&h->d_tri_shade, s->tri_shade, (size_t)s->n_tris * sizeof(GrtTriShade)))) return rc;
+    if (s->tri_v64 && (rc = upload(&h->d_tri_v64, s->tri_v64, (size_t)s->n_tris * 9 * sizeof(double)))) return rc;
+    if ((rc = upload(&h->d_texels, s->texels, (size_t)s->n_texel_bytes))) return rc;
+    if ((rc = upload(&h->d_perlins, s->perlins, (size_t)s->n_perlins * sizeof(GrtPerlin)))) return rc;
     ds.blob = (const unsigned char*)h->d_blob;
     ds.tris = (const GrtTri*)h->d_tris;
     ds.tri_shade = (const GrtTriShade*)h->d_tri_shade;
@@ -669,6 +703,7 @@ extern "C" int grt_scene_upload(const GrtScene* s, int device, GrtSceneHandle* o
     CUDA_TRY(grt_dev_alloc((void**)&h->d_counter, 256));
     h->staged = ds.stage_bytes == 0 ? 0 : (ds.stage_bytes == ds.blob_bytes ? 2 : 1);
     CUDA_TRY(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));   // (cudaGetDeviceProperties takes milliseconds)
+    guard.h = nullptr;
     *out = h;
     return GRT_OK;
 }

@@ -7,6 +7,7 @@
 // atomics as each pixel is retired — the exchange is spread over the whole render (12.6 MB of 4-byte reductions over
 // tens of milliseconds) instead of following it, and no collective runs at all.
 // Fallback (no peer access): private buffers and ONE ncclReduce(sum, root = devices[0]) before tonemap.
+// The devices render concurrently (one host thread each); kernel_ms is the slowest device's e0..e1 time.
 // (bench.py instead runs one process per GPU and reduces through torch.distributed's NCCL communicator.)
 //
 // NCCL is bound at run time with dlopen so that libgrt_cuda has no link-time
@@ -17,6 +18,7 @@
 #include <stdlib.h>
 #include <string>
 #include <vector>
+#include <thread>
 #include "grt_internal.h"
 
 namespace {
@@ -116,18 +118,32 @@ extern "C" int grt_render_multi(const GrtScene* scene, const GrtCamera* cam, con
     }
     if (n > 1 && !fused) { NC(g_nccl.CommInitAll(comms.data(), n, devices)); comms_ok = true; }
 
-    // every device renders its strata shard, concurrently
-    for (int g = 0; g < n; g++) {
-        GrtOptions o = *opt;
-        uint32_t base_stride = opt->sample_stride ? opt->sample_stride : 1u;
-        o.sample_first = opt->sample_first + (uint32_t)g * base_stride;
-        o.sample_stride = base_stride * (uint32_t)n;
-        o.device = devices[g];
-        if (fused) o.flags |= GRT_OPT_ATOMIC_SUM;
-        CU(cudaSetDevice(devices[g]));
-        CU(cudaEventRecord(e0[g], st[g]));
-        rc = grt_render_device(hs[g], cam, &o, fused ? d_shared : d_sum[g], st[g], nullptr);
-        if (rc) goto done;
+    // every device renders its strata shard, concurrently: one host thread per device, because the wavefront variant's
+    // bounce loop blocks its caller (it reads the live-path counter back between graph launches) — issued from one
+    // thread the devices would render one after another
+    {
+        std::vector<int> rcs(n, GRT_OK);
+        std::vector<std::string> errs(n);
+        auto work = [&](int g) {
+            GrtOptions o = *opt;
+            uint32_t base_stride = opt->sample_stride ? opt->sample_stride : 1u;
+            o.sample_first = opt->sample_first + (uint32_t)g * base_stride;
+            o.sample_stride = base_stride * (uint32_t)n;
+            o.device = devices[g];
+            if (fused) o.flags |= GRT_OPT_ATOMIC_SUM;
+            cudaError_t e = cudaSetDevice(devices[g]);
+            if (e == cudaSuccess) e = cudaEventRecord(e0[g], st[g]);
+            if (e != cudaSuccess) { rcs[g] = GRT_E_CUDA; errs[g] = cudaGetErrorString(e); return; }
+            rcs[g] = grt_render_device(hs[g], cam, &o, fused ? d_shared : d_sum[g], st[g], nullptr);
+            if (rcs[g]) errs[g] = grt_last_error();   // the error text is thread-local: carry it to the caller
+        };
+        if (n == 1) work(0);
+        else {
+            std::vector<std::thread> th;
+            for (int g = 0; g < n; g++) th.emplace_back(work, g);
+            for (auto& t : th) t.join();
+        }
+        for (int g = 0; g < n; g++) if (rcs[g]) { grt_set_error(errs[g]); rc = rcs[g]; goto done; }
     }
     if (n > 1 && !fused) {
         NC(g_nccl.GroupStart());

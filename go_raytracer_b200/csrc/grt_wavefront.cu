@@ -315,8 +315,8 @@ static int wf_run(GrtSceneHandle h, WfParams& P, cudaStream_t st, uint32_t* h_co
     // Triangle meshes: persistent extend with dynamic ray fetch (166 -> 271 Mpaths/s on the 1M-triangle config).  The
     // sphere / box BVHs of the book scenes have short, even traversals and expensive leaves; the plain
     // one-thread-per-slot extend is faster there (311 vs 252 and 720 vs 633 Mpaths/s; profiles/README.md).
-    constexpr bool can_dyn = (FEAT & F_NODE) != 0 && (FEAT & F_TRI) != 0;
-    bool dyn = can_dyn && P.scene.n_tris >= 1024u;
+    constexpr bool can_dyn = (FEAT & F_NODE) != 0;
+    bool dyn = can_dyn && (FEAT & F_TRI) != 0 && P.scene.n_tris >= 1024u;
     if (const char* e = getenv("GRT_WF_DYN")) dyn = can_dyn && (atoi(e) == 2 || (dyn && atoi(e) != 0));   // 0: never, 2: whenever compiled in
     const bool staged = grt_internal_staged(h) == 2 && !dyn;   // whole-blob staging or none
     const unsigned dyn_blocks = (unsigned)grt_internal_sm_count(h) * WF_DYN_MIN_BLOCKS;

@@ -1,0 +1,362 @@
+// wide_bvh.hpp — the device-internal 4-wide BVH, built at upload from the ABI's binary GrtNode array.
+//
+// The ABI (include/grt.h) carries BuildBVH's binary tree in the reference's child order (bvh.go:35-61).  A binary
+// tree costs one dependent memory round trip per level, and on the 10^5..10^6-node trees of configs C4/C5 the extend
+// kernel was bound by exactly that latency (profiles/README.md, round 1).  Here every binary node absorbs
+// grandchildren until it has four children (the child with the largest box is opened first), children keep their
+// left-to-right order, and each child — inner node OR leaf — carries its own box:
+//
+//   * the closest hit is unchanged: boxes only cull, and every box is conservative (rounded outwards);
+//   * a subtree that contains a constantMedium is flagged "in order": its children are visited in the reference's
+//     order, because a medium test draws a random number (medium.go:47) and the draw index must not depend on the
+//     visiting order; a culled medium never reaches its draw (both boundary hits lie inside its box), so culling is
+//     unobservable there too;
+//   * everywhere else children are visited nearest first; which of two EXACTLY equidistant primitives wins then
+//     differs from bvh.go:73-79 — the documented tie, already true of round 1's axis hints;
+//   * a leaf run of up to 8 consecutive primitives is named in the child ref itself (DREF_RUN), so reaching the
+//     primitives costs no list-entry fetch.
+//
+// Node layout (128 bytes = one L1 line, 8 x float4): lo.x[4] lo.y[4] lo.z[4] hi.x[4] hi.y[4] hi.z[4] ref[4] meta[4];
+// meta[0] bit 0 = children may be visited nearest first, meta[1] = number of children.  Empty slots hold the empty
+// box (+inf, -inf) and a NONE ref.  Nodes are numbered breadth first from the roots, so the first k nodes are the
+// top of the tree: that prefix is what the kernels stage in shared memory.
+#pragma once
+#include <stdint.h>
+#include <math.h>
+#include <string.h>
+#include <algorithm>
+#include <deque>
+#include <limits>
+#include <string>
+#include <vector>
+#include "../../include/grt.h"
+
+namespace grt {
+namespace wide {
+
+// device-internal child ref of a primitive run: bit 31 | type << 28 | (count - 1) << 25 | first index (25 bits)
+#define GRT_DREF_RUN_BIT 0x80000000u
+#define GRT_DREF_RUN_MAX_COUNT 8u
+#define GRT_DREF_RUN_INDEX_BITS 25u
+#define GRT_DREF_RUN_INDEX_MASK ((1u << GRT_DREF_RUN_INDEX_BITS) - 1u)
+#define GRT_WNODE_FLOATS 32
+
+struct Box {
+    double lo[3], hi[3];
+    static Box none() { Box b; for (int a = 0; a < 3; a++) { b.lo[a] = std::numeric_limits<double>::infinity(); b.hi[a] = -std::numeric_limits<double>::infinity(); } return b; }
+    static Box all() { Box b; for (int a = 0; a < 3; a++) { b.lo[a] = -std::numeric_limits<double>::infinity(); b.hi[a] = std::numeric_limits<double>::infinity(); } return b; }
+    void add(const double p[3]) { for (int a = 0; a < 3; a++) { lo[a] = fmin(lo[a], p[a]); hi[a] = fmax(hi[a], p[a]); } }
+    void add(const Box& o) { for (int a = 0; a < 3; a++) { lo[a] = fmin(lo[a], o.lo[a]); hi[a] = fmax(hi[a], o.hi[a]); } }
+    bool empty() const { return !(lo[0] <= hi[0] && lo[1] <= hi[1] && lo[2] <= hi[2]); }
+    bool finite() const { for (int a = 0; a < 3; a++) if (!std::isfinite(lo[a]) || !std::isfinite(hi[a])) return false; return true; }
+    double area() const {
+        if (empty()) return 0.0;
+        if (!finite()) return std::numeric_limits<double>::infinity();
+        double x = hi[0] - lo[0], y = hi[1] - lo[1], z = hi[2] - lo[2];
+        return x * y + y * z + z * x;
+    }
+};
+
+struct Result {
+    std::vector<float> wnodes;         // GRT_WNODE_FLOATS per node
+    std::vector<uint32_t> node_map;    // binary node index -> wide node index (0xFFFFFFFF: absorbed into its parent)
+    uint32_t n_wide = 0;
+    int need_main = 0, need_boundary = 0;   // traversal stack entries a closest-hit query can hold at once
+    std::string error;
+};
+
+class Builder {
+   public:
+    // nodes / entries / media: already remapped to device refs (LIST refs index `entries`, pairs {first ref | LAST, count})
+    Builder(const GrtScene* s, const std::vector<GrtNode>& nodes, const std::vector<uint32_t>& entries, const std::vector<GrtMedium>& media)
+        : S(s), N(nodes), E(entries), M(media) {}
+
+    bool run(uint32_t root, Result& R) {
+        const uint32_t NONE_IDX = 0xFFFFFFFFu;
+        R.node_map.assign(N.size(), NONE_IDX);
+        hasMedium.assign(N.size(), -1);
+        std::deque<uint32_t> queue;
+        auto enqueue = [&](uint32_t b) -> uint32_t {
+            if (R.node_map[b] == NONE_IDX) { R.node_map[b] = R.n_wide++; queue.push_back(b); }
+            return R.node_map[b];
+        };
+        // roots: every NODE ref held outside the node array
+        if (type(root) == GRT_REF_NODE) enqueue(idx(root));
+        for (size_t k = 0; k + 1 < E.size(); k += 2) { uint32_t r = E[k] & ~GRT_LIST_LAST; if (type(r) == GRT_REF_NODE) enqueue(idx(r)); }
+        for (const GrtMedium& m : M) if (type(m.boundary) == GRT_REF_NODE) enqueue(idx(m.boundary));
+        std::vector<uint32_t> kids;
+        while (!queue.empty()) {
+            const uint32_t b = queue.front();
+            queue.pop_front();
+            const uint32_t w = R.node_map[b];
+            if (R.wnodes.size() < (size_t)(w + 1) * GRT_WNODE_FLOATS) R.wnodes.resize((size_t)(w + 1) * GRT_WNODE_FLOATS, 0.0f);
+            kids.clear();
+            pushChildren(kids, b);
+            // open the child with the largest box until there are four (children keep their left-to-right order)
+            while (kids.size() < 4) {
+                int best = -1;
+                double bestArea = -1.0;
+                for (size_t i = 0; i < kids.size(); i++) {
+                    if (type(kids[i]) != GRT_REF_NODE) continue;
+                    std::vector<uint32_t> sub;
+                    pushChildren(sub, idx(kids[i]));
+                    if (kids.size() - 1 + sub.size() > 4) continue;
+                    double a = nodeBox(idx(kids[i])).area();
+                    if (a > bestArea) { bestArea = a; best = (int)i; }
+                }
+                if (best < 0) break;
+                std::vector<uint32_t> sub;
+                pushChildren(sub, idx(kids[best]));
+                kids.erase(kids.begin() + best);
+                kids.insert(kids.begin() + best, sub.begin(), sub.end());
+            }
+            // write the node
+            float* d = R.wnodes.data() + (size_t)w * GRT_WNODE_FLOATS;
+            const float INF = std::numeric_limits<float>::infinity();
+            uint32_t refs[4], meta[4] = {0, 0, 0, 0};
+            for (int k = 0; k < 4; k++) {
+                for (int a = 0; a < 3; a++) { d[4 * a + k] = INF; d[12 + 4 * a + k] = -INF; }
+                refs[k] = GRT_MAKE_REF(GRT_REF_NONE, 0);
+            }
+            bool ordered = !subtreeHasMedium(GRT_MAKE_REF(GRT_REF_NODE, b));
+            uint32_t nk = 0;
+            for (uint32_t c : kids) {
+                if (type(c) == GRT_REF_NONE) continue;
+                Box bx;
+                uint32_t ref = c;
+                if (type(c) == GRT_REF_NODE) {
+                    // the ABI's node boxes are the fp64 geometry rounded outwards; the fp32 primitives the device tests
+                    // (v0, e0, e1 rounded separately) can sit an ulp OF THE LARGEST COORDINATE outside of them
+                    bx = nodeBox(idx(c));
+                    grow(bx, 5e-7);
+                    ref = GRT_MAKE_REF(GRT_REF_NODE, enqueue(idx(c)));
+                }
+                else { bx = refBox(c); ref = asRun(c); }
+                if (bx.empty()) continue;    // nothing below this child can be hit
+                for (int a = 0; a < 3; a++) { d[4 * a + nk] = down(bx.lo[a]); d[12 + 4 * a + nk] = up(bx.hi[a]); }
+                refs[nk++] = ref;
+            }
+            meta[0] = ordered ? 1u : 0u;
+            meta[1] = nk;
+            memcpy(d + 24, refs, 16);
+            memcpy(d + 28, meta, 16);
+        }
+        // stack needs
+        needW.assign(R.n_wide, -1);
+        Rp = &R;
+        R.need_main = needRef(wideRef(root)) + 2;
+        R.need_boundary = 0;
+        for (const GrtMedium& m : M) R.need_boundary = std::max(R.need_boundary, needRef(wideRef(m.boundary)) + 2);
+        return R.error.empty();
+    }
+
+    // a ref as the device sees it: NODE refs index the wide array
+    uint32_t wideRef(uint32_t r) const {
+        if (type(r) == GRT_REF_NODE) return GRT_MAKE_REF(GRT_REF_NODE, Rp->node_map[idx(r)]);
+        return r;
+    }
+
+   private:
+    const GrtScene* S;
+    const std::vector<GrtNode>& N;
+    const std::vector<uint32_t>& E;
+    const std::vector<GrtMedium>& M;
+    std::vector<int> hasMedium, needW;
+    Result* Rp = nullptr;
+
+    static uint32_t type(uint32_t r) { return GRT_REF_TYPE(r); }
+    static uint32_t idx(uint32_t r) { return r & GRT_REF_MASK; }
+    static bool isPrim(uint32_t t) { return t == GRT_REF_SPHERE || t == GRT_REF_QUAD || t == GRT_REF_TRI || t == GRT_REF_BOX; }
+
+    // outward rounding with a margin of a few ulps (the device slab test is fp32)
+    static float down(double x) {
+        if (!std::isfinite(x)) return (float)x;
+        float f = (float)(x - 4e-7 * fabs(x) - 1e-30);
+        if ((double)f > x) f = nextafterf(f, -std::numeric_limits<float>::infinity());
+        return nextafterf(f, -std::numeric_limits<float>::infinity());
+    }
+    static float up(double x) {
+        if (!std::isfinite(x)) return (float)x;
+        float f = (float)(x + 4e-7 * fabs(x) + 1e-30);
+        if ((double)f < x) f = nextafterf(f, std::numeric_limits<float>::infinity());
+        return nextafterf(f, std::numeric_limits<float>::infinity());
+    }
+
+    // children of binary node b in the reference's order; a span-1 node names one object twice (bvh.go:44-46):
+    // testing a surface twice cannot change the closest hit, a medium draws per test and is kept twice
+    void pushChildren(std::vector<uint32_t>& out, uint32_t b) {
+        const uint32_t l = N[b].left & ~GRT_NODE_HINT_BIT, r = N[b].right & ~GRT_NODE_HINT_BIT;
+        out.push_back(l);
+        if (r != l || subtreeHasMedium(l)) out.push_back(r);
+    }
+
+    Box nodeBox(uint32_t b) const {
+        Box x;
+        for (int a = 0; a < 3; a++) { x.lo[a] = N[b].bmin[a]; x.hi[a] = N[b].bmax[a]; }
+        return x;
+    }
+
+    bool subtreeHasMedium(uint32_t r) {
+        switch (type(r)) {
+            case GRT_REF_MEDIUM: return true;
+            case GRT_REF_NODE: {
+                // iterative post-order so a million-node tree does not recurse a million deep
+                const uint32_t b0 = idx(r);
+                if (hasMedium[b0] >= 0) return hasMedium[b0] != 0;
+                std::vector<uint32_t> st{b0};
+                while (!st.empty()) {
+                    const uint32_t b = st.back();
+                    if (hasMedium[b] >= 0) { st.pop_back(); continue; }
+                    const uint32_t c[2] = {N[b].left & ~GRT_NODE_HINT_BIT, N[b].right & ~GRT_NODE_HINT_BIT};
+                    bool ready = true, any = false;
+                    for (int k = 0; k < 2; k++) {
+                        if (type(c[k]) == GRT_REF_NODE) {
+                            if (hasMedium[idx(c[k])] < 0) { st.push_back(idx(c[k])); ready = false; }
+                            else any = any || hasMedium[idx(c[k])] != 0;
+                        } else any = any || subtreeHasMedium(c[k]);
+                    }
+                    if (ready) { hasMedium[b] = any ? 1 : 0; st.pop_back(); }
+                }
+                return hasMedium[b0] != 0;
+            }
+            case GRT_REF_LIST: {
+                for (uint32_t k = idx(r);; k++) {
+                    const uint32_t e = E[2 * k];
+                    if (subtreeHasMedium(e & ~GRT_LIST_LAST)) return true;
+                    if (e & GRT_LIST_LAST) break;
+                }
+                return false;
+            }
+        }
+        return false;
+    }
+
+    // ---- boxes of things that are not inner nodes -------------------------------------------------------------
+    Box primBox(uint32_t t, uint32_t i) const {
+        Box b = Box::none();
+        if (t == GRT_REF_SPHERE) {   // objects.go:23-37
+            const GrtSphere& s = S->spheres[i];
+            for (int k = 0; k < 2; k++) {
+                double lo[3], hi[3];
+                for (int a = 0; a < 3; a++) { double c = s.c0[a] + (double)k * (double)s.dc[a]; lo[a] = c - fabs(s.r); hi[a] = c + fabs(s.r); }
+                b.add(lo); b.add(hi);
+            }
+            grow(b, 1e-6);
+        } else if (t == GRT_REF_TRI) {   // objects.go:317-354
+            const GrtTri& tr = S->tris[i];
+            double v0[3], v1[3], v2[3];
+            for (int a = 0; a < 3; a++) { v0[a] = tr.v0[a]; v1[a] = (double)tr.v0[a] + tr.e0[a]; v2[a] = (double)tr.v0[a] + tr.e1[a]; }
+            b.add(v0); b.add(v1); b.add(v2);
+            if (S->tri_v64) { const double* v = S->tri_v64 + 9 * (size_t)i; b.add(v); b.add(v + 3); b.add(v + 6); }
+            grow(b, 1e-6);
+        } else if (t == GRT_REF_QUAD) {   // objects.go:129-147; u, v recovered from alpha = A.(p-Q), beta = B.(p-Q)
+            const GrtQuad& q = S->quads[i];
+            const double n[3] = {q.n[0], q.n[1], q.n[2]}, A[3] = {q.A[0], q.A[1], q.A[2]}, B[3] = {q.B[0], q.B[1], q.B[2]};
+            double bn[3], na[3];
+            cross(B, n, bn); cross(n, A, na);
+            const double su = dot(A, bn), sv = dot(B, na);
+            if (!(fabs(su) > 1e-300) || !(fabs(sv) > 1e-300) || !std::isfinite(su) || !std::isfinite(sv)) return Box::all();
+            double p[4][3];
+            for (int a = 0; a < 3; a++) {
+                const double u = bn[a] / su, v = na[a] / sv;
+                p[0][a] = q.Q[a]; p[1][a] = q.Q[a] + u; p[2][a] = q.Q[a] + v; p[3][a] = q.Q[a] + u + v;
+            }
+            for (int k = 0; k < 4; k++) b.add(p[k]);
+            grow(b, 1e-4);
+        } else if (t == GRT_REF_BOX) {   // objects.go:208-240 under the baked rotateY + translate
+            const GrtBox& x = S->boxes[i];
+            for (int k = 0; k < 8; k++) {
+                const double ox = (k & 1) ? x.mx[0] : x.mn[0], oy = (k & 2) ? x.mx[1] : x.mn[1], oz = (k & 4) ? x.mx[2] : x.mn[2];
+                const double p[3] = {(double)x.rc * ox + (double)x.rs * oz + x.T[0], oy + x.T[1], -(double)x.rs * ox + (double)x.rc * oz + x.T[2]};
+                b.add(p);
+            }
+            grow(b, 1e-5);
+        }
+        return b;
+    }
+    static void grow(Box& b, double rel) {
+        if (b.empty()) return;
+        for (int a = 0; a < 3; a++) {
+            const double m = rel * (fabs(b.lo[a]) + fabs(b.hi[a]) + (b.hi[a] - b.lo[a])) + 1e-7;
+            b.lo[a] -= m; b.hi[a] += m;
+        }
+    }
+    static void cross(const double a[3], const double b[3], double o[3]) { o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0]; }
+    static double dot(const double a[3], const double b[3]) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+
+    Box refBox(uint32_t r, int depth = 0) const {
+        if (depth > 16) return Box::all();
+        const uint32_t t = type(r), i = idx(r);
+        if (isPrim(t)) return primBox(t, i);
+        if (t == GRT_REF_NODE) return nodeBox(i);
+        if (t == GRT_REF_MEDIUM) return refBox(M[i].boundary, depth + 1);
+        if (t == GRT_REF_LIST) {
+            Box b = Box::none();
+            for (uint32_t k = i;; k++) {
+                const uint32_t e = E[2 * k], cnt = E[2 * k + 1], first = e & ~GRT_LIST_LAST;
+                if (isPrim(type(first))) for (uint32_t j = 0; j < cnt; j++) b.add(primBox(type(first), idx(first) + j));
+                else b.add(refBox(first, depth + 1));
+                if (e & GRT_LIST_LAST) break;
+            }
+            return b;
+        }
+        return Box::none();
+    }
+
+    // a child that is one short run of primitives is named directly (no list-entry fetch on the device)
+    uint32_t asRun(uint32_t r) const {
+        uint32_t first = r, cnt = 1;
+        if (type(r) == GRT_REF_LIST) {
+            const uint32_t e = E[2 * idx(r)];
+            if (!(e & GRT_LIST_LAST)) return r;
+            first = e & ~GRT_LIST_LAST; cnt = E[2 * idx(r) + 1];
+        }
+        if (!isPrim(type(first)) || cnt < 1 || cnt > GRT_DREF_RUN_MAX_COUNT || idx(first) + cnt - 1 > GRT_DREF_RUN_INDEX_MASK) return r;
+        return GRT_DREF_RUN_BIT | (type(first) << GRT_REF_SHIFT) | ((cnt - 1) << GRT_DREF_RUN_INDEX_BITS) | idx(first);
+    }
+
+    // ---- traversal stack need (entries held at once, worst case over visiting orders) ------------------------------
+    int needRef(uint32_t r, int depth = 0) {
+        if (depth > 64) { Rp->error = "scene nesting too deep"; return 1 << 20; }
+        if (r & GRT_DREF_RUN_BIT) return 0;
+        switch (type(r)) {
+            case GRT_REF_NODE: return needWide(idx(r), depth);
+            case GRT_REF_LIST: {
+                int need = 0;
+                for (uint32_t k = idx(r);; k++) {
+                    const uint32_t e = E[2 * k];
+                    need = std::max(need, 1 + needRef(wideRef(e & ~GRT_LIST_LAST), depth + 1));   // the rest of the list waits on the stack
+                    if (e & GRT_LIST_LAST) break;
+                }
+                return need;
+            }
+        }
+        return 0;   // primitives; a medium's boundary query runs on its own stack (need_boundary)
+    }
+    int needWide(uint32_t w0, int depth) {
+        if (needW[w0] >= 0) return needW[w0];
+        // iterative post-order over wide nodes
+        std::vector<uint32_t> st{w0};
+        while (!st.empty()) {
+            const uint32_t w = st.back();
+            if (needW[w] >= 0) { st.pop_back(); continue; }
+            const float* d = Rp->wnodes.data() + (size_t)w * GRT_WNODE_FLOATS;
+            uint32_t refs[4], meta[4];
+            memcpy(refs, d + 24, 16); memcpy(meta, d + 28, 16);
+            bool ready = true;
+            int mx = 0;
+            for (uint32_t k = 0; k < meta[1]; k++) {
+                const uint32_t c = refs[k];
+                if (!(c & GRT_DREF_RUN_BIT) && type(c) == GRT_REF_NODE) {
+                    if (needW[idx(c)] < 0) { st.push_back(idx(c)); ready = false; }
+                    else mx = std::max(mx, needW[idx(c)]);
+                } else mx = std::max(mx, needRef(c, depth + 1));
+            }
+            if (ready) { needW[w] = (int)meta[1] - 1 + mx; if (needW[w] < 0) needW[w] = 0; st.pop_back(); }
+        }
+        return needW[w0];
+    }
+};
+
+}  // namespace wide
+}  // namespace grt

@@ -183,7 +183,7 @@ def _check_direct_irradiance(render, trace_of):
     rays = PU.primary_batch(cfg, (0, 0, cam.width, cam.height))
     h = trace_of(sc)(rays)
     p = h["p"].astype(np.float64)
-    on_floor = (np.abs(p[:, 1]) < 1e-6) & (h["t"] < 1e30)
+    on_floor = (np.abs(p[:, 1]) < 1e-3) & np.isfinite(h["t"]) & (h["t"] < 1e30)      # the floor is y = 0 (fp32 hit points on the GPU side)
     expect = (RHO * LE * form_factor(p[:, 0], p[:, 2])).reshape(cam.height, cam.width)
     m = _erode(on_floor.reshape(cam.height, cam.width), 1)
     assert m.sum() > 500

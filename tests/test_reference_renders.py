@@ -67,8 +67,10 @@ def test_cuda_render_reproduces_the_go_renders(name, variant):
     cam = g.derive_camera(cfg)
     v = g.GRT_VARIANT_MEGAKERNEL if variant == "mega" else g.GRT_VARIANT_WAVEFRONT
     sums, rgb8, _ = g.DeviceScene(s).render(cam, seed=0xBEEF, variant=v, want_rgb8=True)
-    # the device tonemap (color.go:14-46) is what a caller writes to the PPM; it must be the host formula on the sums
-    assert np.array_equal(rgb8.astype(np.float64), RU.print_color(sums, cam.spp_sqrt ** 2))
+    # the device tonemap (color.go:14-46, fp32) is what a caller writes to the PPM: the host formula (fp64) on the same
+    # sums, up to one code value where sqrt(x) * 256 lands within fp32 rounding of an integer
+    d = np.abs(rgb8.astype(np.float64) - RU.print_color(sums, cam.spp_sqrt ** 2))
+    assert d.max() <= 1 and (d == 0).mean() > 0.999, (d.max(), (d == 0).mean())
     dmean, dblock, jm, jb = RU.assert_matches_reference(rgb8.astype(np.float64), name, f"CUDA {variant}")
     print(f"{name}/{variant}: channel-mean diff {dmean.round(3)}, block diff {dblock:.3f}; through the same JPEG tables {jm.round(3)}, {jb:.3f} (/255)")
 
