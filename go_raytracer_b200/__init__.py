@@ -7,9 +7,9 @@ Go API used by tests and bench: `Scene` (package hittable's constructors),
 """
 from ._native import (GrtError, GrtCameraConfig, GrtCamera, GrtOptions, GrtStats, GrtScene, RAY_DTYPE, HIT_DTYPE,
                       GRT_VARIANT_MEGAKERNEL, GRT_VARIANT_WAVEFRONT, GRT_VARIANT_AUTO, GRT_NO_ID, lib, LIB_PATH, bvh_order)
-from .scene import Scene, builtin_scene, SCENE_NAMES, PERLIN, MARBLE, TURBULENT
+from .scene import Scene, builtin_scene, decode_jpeg, load_image, SCENE_NAMES, PERLIN, MARBLE, TURBULENT
 from .camera import Camera, DeviceScene, derive_camera, write_ppm, write_p6, write_png
 
 __all__ = ["GrtError", "GrtCameraConfig", "GrtCamera", "GrtOptions", "GrtStats", "GrtScene", "RAY_DTYPE", "HIT_DTYPE",
-           "GRT_VARIANT_MEGAKERNEL", "GRT_VARIANT_WAVEFRONT", "GRT_VARIANT_AUTO", "GRT_NO_ID", "lib", "LIB_PATH", "bvh_order", "Scene", "builtin_scene",
+           "GRT_VARIANT_MEGAKERNEL", "GRT_VARIANT_WAVEFRONT", "GRT_VARIANT_AUTO", "GRT_NO_ID", "lib", "LIB_PATH", "bvh_order", "Scene", "builtin_scene", "decode_jpeg", "load_image",
            "SCENE_NAMES", "PERLIN", "MARBLE", "TURBULENT", "Camera", "DeviceScene", "derive_camera", "write_ppm", "write_p6", "write_png"]

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("GRT_CUDA_LIB") or os.path.join(_HERE, "csrc", "libgrt
 
 GRT_OK, GRT_E_INVALID, GRT_E_NO_DEVICE, GRT_E_CUDA, GRT_E_UNSUPPORTED, GRT_E_NCCL = 0, -1, -2, -3, -4, -5
 GRT_VARIANT_MEGAKERNEL, GRT_VARIANT_WAVEFRONT, GRT_VARIANT_AUTO = 0, 1, 2
-GRT_OPT_STATS = 1
+GRT_OPT_STATS, GRT_OPT_ATOMIC_SUM, GRT_OPT_TIMING = 1, 2, 4
 GRT_NO_ID = 0xFFFFFFFF
 REF_SHIFT, REF_MASK = 28, 0x0FFFFFFF
 REF_NODE, REF_SPHERE, REF_QUAD, REF_TRI, REF_LIST, REF_MEDIUM, REF_BOX, REF_NONE = 0, 1, 2, 3, 4, 5, 6, 7
@@ -69,6 +69,12 @@ class GrtStats(C.Structure):
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+class GrtTiming(C.Structure):
+    """grt_last_timing: device time per kernel class of the last GRT_OPT_TIMING render (CUDA events)."""
+    _fields_ = [("total_ms", C.c_double), ("generate_ms", C.c_double), ("extend_ms", C.c_double), ("shade_ms", C.c_double),
+                ("extend_launches", C.c_uint64), ("launches", C.c_uint64)]
 
 
 class GrtScene(C.Structure):
@@ -135,7 +141,7 @@ def lib():
     P = C.POINTER
     sig = {
         "grt_abi_version": (i32, []), "grt_device_count": (i32, []), "grt_last_error": (C.c_char_p, []),
-        "grt_launch_count": (u64, []), "grt_bvh_order": (i32, [vp, C.c_uint32, i32, vp]),
+        "grt_launch_count": (u64, []), "grt_last_timing": (i32, [P(GrtTiming)]), "grt_bvh_order": (i32, [vp, C.c_uint32, i32, vp]),
         "grt_scene_upload": (i32, [P(GrtScene), i32, P(vp)]), "grt_scene_free": (i32, [vp]),
         "grt_trace_batch": (i32, [vp, vp, u64, vp]), "grt_trace_batch_device": (i32, [vp, vp, u64, vp, vp]),
         "grt_render": (i32, [vp, P(GrtCamera), P(GrtOptions), vp, vp, P(GrtStats)]),
@@ -144,7 +150,8 @@ def lib():
         "grt_render_multi": (i32, [P(GrtScene), P(GrtCamera), P(GrtOptions), P(i32), i32, vp, vp, P(dbl)]),
         "grt_host_last_error": (C.c_char_p, []), "grt_host_scene_new": (vp, []), "grt_host_scene_free": (None, [vp]),
         "grt_host_solid_color": (i32, [vp, dbl, dbl, dbl]), "grt_host_checkerboard": (i32, [vp, dbl, i32, i32]),
-        "grt_host_image": (i32, [vp, i32, i32, vp]), "grt_host_image_texture": (i32, [vp, i32]),
+        "grt_host_image": (i32, [vp, i32, i32, vp]),
+        "grt_host_decode_jpeg": (i32, [vp, C.c_size_t, P(i32), P(i32), vp, C.c_size_t]), "grt_host_image_texture": (i32, [vp, i32]),
         "grt_host_noise_texture": (i32, [vp, dbl, i32, u64]),
         "grt_host_lambertian": (i32, [vp, i32]), "grt_host_metal": (i32, [vp, dbl, dbl, dbl, dbl]),
         "grt_host_dielectric": (i32, [vp, dbl]), "grt_host_diffuse_light": (i32, [vp, i32]),
@@ -178,10 +185,10 @@ EXPORTED_SYMBOLS = [
     # include/grt.h
     "grt_abi_version", "grt_device_count", "grt_last_error", "grt_scene_upload", "grt_scene_free", "grt_trace_batch",
     "grt_trace_batch_device", "grt_render", "grt_render_device", "grt_tonemap_device", "grt_render_multi",
-    "grt_launch_count", "grt_bvh_order",
+    "grt_launch_count", "grt_last_timing", "grt_bvh_order",
     # include/grt_host.h
     "grt_host_last_error", "grt_host_scene_new", "grt_host_scene_free", "grt_host_solid_color", "grt_host_checkerboard",
-    "grt_host_image", "grt_host_image_texture", "grt_host_noise_texture", "grt_host_lambertian", "grt_host_metal",
+    "grt_host_image", "grt_host_decode_jpeg", "grt_host_image_texture", "grt_host_noise_texture", "grt_host_lambertian", "grt_host_metal",
     "grt_host_dielectric", "grt_host_diffuse_light", "grt_host_isotropic", "grt_host_sphere", "grt_host_motion_sphere",
     "grt_host_quad", "grt_host_box", "grt_host_triangle", "grt_host_list", "grt_host_list_add", "grt_host_bvh",
     "grt_host_translate", "grt_host_rotate_y", "grt_host_constant_medium", "grt_host_set_world", "grt_host_set_lights",

@@ -59,13 +59,14 @@ class DeviceScene:
         return sums, rgb8, (stats.as_dict() if want_stats else None)
 
     def render_device(self, cam, d_rgb_sum_ptr, stream_ptr=0, seed=0xC0FFEE, variant=N.GRT_VARIANT_MEGAKERNEL,
-                      sample_first=0, sample_stride=1, d_stats_ptr=0):
+                      sample_first=0, sample_stride=1, d_stats_ptr=0, flags=0):
         """grt_render_device: accumulate into a device buffer, asynchronously on `stream_ptr`."""
         opt = N.GrtOptions()
         opt.seed, opt.variant, opt.device = int(seed), int(variant), int(self.device)
         opt.sample_first, opt.sample_stride = int(sample_first), int(sample_stride)
+        opt.flags = int(flags)
         if d_stats_ptr:
-            opt.flags = N.GRT_OPT_STATS
+            opt.flags |= N.GRT_OPT_STATS
         N.check(self._L.grt_render_device(self._h, C.byref(cam), C.byref(opt), C.c_void_p(d_rgb_sum_ptr),
                                           C.c_void_p(stream_ptr), C.c_void_p(d_stats_ptr)))
 

@@ -26,8 +26,26 @@ enum : uint32_t {
     // t >= tmin decisions fall back to the fp64 plane when the origin is within fp32 resolution of that plane.
     // The integrator always names the primitive it starts on (self exclusion), which leaves such events at
     // ~1e-7 per segment, and compiles the fallback out of its quad loop.
-    F_TMIN_F64 = 1u << 16
+    F_TMIN_F64 = 1u << 16,
+    // not a scene feature either: the scene arrays are read from global memory (nothing staged in shared memory), so the
+    // traversal fetches them through the read-only path (ld.global.nc, __ldg) instead of generic loads
+    F_GMEM = 1u << 18
 };
+// Which loads take the read-only path: the node fetches always do (F_GMEM); the primitive records only where it paid —
+// ptxas schedules ld.global.nc loads earlier and wider, which cost the all-feature extend kernel 1.1 KB of spills.
+#ifndef GRT_NC_PRIMS
+#define GRT_NC_PRIMS 0
+#endif
+#define GRT_PRIM_NC(FEAT) (GRT_NC_PRIMS != 0 && ((FEAT) & F_GMEM) != 0)
+#ifndef GRT_NC_NODES
+#define GRT_NC_NODES 1
+#endif
+// load through the read-only data path when the pointer is known to be global memory
+template <bool NC, class T>
+__device__ __forceinline__ T ldro(const T* p) {
+    if constexpr (NC) return __ldg(p);
+    else return *p;
+}
 // feature-set variants the kernels are instantiated for (a scene runs on the smallest one that covers it)
 #define V_CORNELL (F_QUAD | F_BOX | F_LIST | F_ROTQUAD | F_QUAD_LIGHT)
 #define V_SMOKE (V_CORNELL | F_MEDIUM | F_ISOTROPIC)
@@ -36,6 +54,10 @@ enum : uint32_t {
 #define V_FULL F_ALL
 #define V_FULL_UNIQ (F_ALL & ~F_DUPIDS)   /* everything, quads excluded by flat ref (no duplicated quad ids) */
 #define GRT_NEEDS_F64(FEAT) (((FEAT) & F_SPHERE) != 0)
+// The fp64 copies of the ray (14 registers) stay live only in the sphere-only variant, where a segment makes ~40 sphere
+// tests; variants that also traverse triangle BVHs convert on the fly (6 cvt + 3 DFMA per sphere test) — in the mesh
+// extend kernel those registers were spilled around every node visit (ncu: local loads + stores = 45 % of its L1 sectors)
+#define GRT_RAY_KEEPS_F64(FEAT) ((((FEAT) & F_SPHERE) != 0) && (((FEAT) & F_TRI) == 0))
 
 // Device-internal quad records, repacked from GrtQuad at upload.
 // Hot (48 B, read by every test): plane, and the interior test folded into two affine forms
@@ -133,7 +155,7 @@ __device__ __forceinline__ void ray_setup(RayD& r, f3 o, f3 d, float time) {
         r.invd = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);  // aabb.go:96 (only box tests use it)
         r.nx = r.invd.x < 0.0f ? 3u : 0u; r.ny = r.invd.y < 0.0f ? 4u : 1u; r.nz = r.invd.z < 0.0f ? 5u : 2u;
     }
-    if (GRT_NEEDS_F64(FEAT)) {
+    if (GRT_RAY_KEEPS_F64(FEAT)) {
         r.o64 = tod3(o); r.d64 = tod3(d);
         r.a64 = dot(r.d64, r.d64);
     }
@@ -182,17 +204,29 @@ __device__ __forceinline__ bool box_hit(float lx, float ly, float lz, float hx, 
 // the roots use the cancellation-free pair {c/q, q/a}, q = h + sign(h) sqrt(disc),
 // which equals {(h-s)/a, (h+s)/a} of the reference up to rounding.
 // `self`: the ray origin lies on this sphere; exact arithmetic has c == 0.
-__device__ __forceinline__ bool sphere_roots(const GrtSphere& s, const RayD& r, bool self, float& nearr, float& farr) {
+template <bool KEEPS_F64, bool NC = false>
+__device__ __forceinline__ bool sphere_roots(const GrtSphere& sg, const RayD& r, bool self, float& nearr, float& farr) {
+    const d3 o64 = KEEPS_F64 ? r.o64 : tod3(r.o), d64 = KEEPS_F64 ? r.d64 : tod3(r.d);
+    const double a64 = KEEPS_F64 ? r.a64 : dot(d64, d64);
+    // c0.xy | c0.z, r | dc.xyz, mat: three 16-byte loads of the 64-byte record
+    struct { double c0[3], r; float dc[3]; } s;
+    if constexpr (NC) {
+        const double2 c01 = __ldg((const double2*)&sg.c0[0]), c2r = __ldg((const double2*)&sg.c0[2]);
+        const float4 dcm = __ldg((const float4*)&sg.dc[0]);
+        s.c0[0] = c01.x; s.c0[1] = c01.y; s.c0[2] = c2r.x; s.r = c2r.y; s.dc[0] = dcm.x; s.dc[1] = dcm.y; s.dc[2] = dcm.z;
+    } else {
+        s.c0[0] = sg.c0[0]; s.c0[1] = sg.c0[1]; s.c0[2] = sg.c0[2]; s.r = sg.r; s.dc[0] = sg.dc[0]; s.dc[1] = sg.dc[1]; s.dc[2] = sg.dc[2];
+    }
     double cx = s.c0[0] + (double)r.time * (double)s.dc[0];
     double cy = s.c0[1] + (double)r.time * (double)s.dc[1];
     double cz = s.c0[2] + (double)r.time * (double)s.dc[2];
-    double ocx = cx - r.o64.x, ocy = cy - r.o64.y, ocz = cz - r.o64.z;
-    double h = r.d64.x * ocx + r.d64.y * ocy + r.d64.z * ocz;
+    double ocx = cx - o64.x, ocy = cy - o64.y, ocz = cz - o64.z;
+    double h = d64.x * ocx + d64.y * ocy + d64.z * ocz;
     double c = ocx * ocx + ocy * ocy + ocz * ocz - s.r * s.r;
     if (self) c = 0.0;
-    double disc = h * h - r.a64 * c;
+    double disc = h * h - a64 * c;
     if (disc < 0) return false;
-    float hf = (float)h, af = (float)r.a64, cf = (float)c;
+    float hf = (float)h, af = (float)a64, cf = (float)c;
     float sq = sqrtf((float)disc);
     if (hf >= 0) { float q = hf + sq; farr = q / af; nearr = cf / q; }
     else { float q = hf - sq; nearr = q / af; farr = cf / q; }
@@ -208,9 +242,10 @@ __device__ __forceinline__ bool sphere_pick(float nearr, float farr, float tmin,
     t_out = root;
     return true;
 }
+template <bool KEEPS_F64, bool NC = false>
 __device__ __forceinline__ bool sphere_hit(const GrtSphere& s, const RayD& r, float tmin, float tmax, bool self, float& t_out) {
     float nearr, farr;
-    if (!sphere_roots(s, r, self, nearr, farr)) return false;
+    if (!sphere_roots<KEEPS_F64, NC>(s, r, self, nearr, farr)) return false;
     return sphere_pick(nearr, farr, tmin, tmax, t_out);
 }
 
@@ -230,8 +265,9 @@ __device__ __forceinline__ float fast_div(float x, float y) {
 // arithmetic in every test).
 // `uncertain` is set when the plane distance at tmin, D - n.(o + tmin d), is within fp32 rounding of zero (the
 // origin lies almost on this plane): the accept/reject decision t >= tmin then needs the fp64 plane.
+template <bool NC = false>
 __device__ __forceinline__ bool quad_hit(const DQuadHot* q, const RayD& r, float tmin, float tmax, float& t_out, float& a_out, float& b_out, bool& uncertain) {
-    const float4 P = q->plane, A = q->A, B = q->B;
+    const float4 P = ldro<NC>(&q->plane), A = ldro<NC>(&q->A), B = ldro<NC>(&q->B);
     const float denom = P.x * r.d.x + P.y * r.d.y + P.z * r.d.z;
     const float num = P.w - (P.x * r.o.x + P.y * r.o.y + P.z * r.o.z);
     const float t = fast_div(num, denom);          // 2 ulp, far inside the 1e-5 budget
@@ -279,9 +315,10 @@ __device__ __forceinline__ float quad_refine_t(const DQuadCold* q, const RayD& r
 // `excl_face`: face of THIS box the ray starts on (-1 if none).  `near_tmin` reports a candidate
 // within fp32 resolution of tmin (see F_TMIN_F64).
 struct BoxSlab { float t_enter, t_exit, d_enter, d_exit; int f_enter, f_exit; };
+template <bool NC = false>
 __device__ __forceinline__ bool box_prim_slab(const GrtBox* bx, const RayD& r, BoxSlab& o) {
-    const float4 b0 = *(const float4*)&bx->mn[0], b1 = *(const float4*)&bx->mx[0], b2 = *(const float4*)&bx->T[0];
-    const float rs = bx->rs, rc = b2.w;
+    const float4 b0 = ldro<NC>((const float4*)&bx->mn[0]), b1 = ldro<NC>((const float4*)&bx->mx[0]), b2 = ldro<NC>((const float4*)&bx->T[0]);
+    const float rs = ldro<NC>(&bx->rs), rc = b2.w;
     const float px = r.o.x - b2.x, py = r.o.y - b2.y, pz = r.o.z - b2.z;
     const float ox = rc * px - rs * pz, oz = rs * px + rc * pz;          // rayTranslationHelper, transformation.go:79-85
     const float dx = rc * r.d.x - rs * r.d.z, dz = rs * r.d.x + rc * r.d.z, dy = r.d.y;
@@ -316,15 +353,42 @@ __device__ __forceinline__ int box_prim_pick(const BoxSlab& o, float tmin, float
     if (tmin <= o.t_exit && o.t_exit <= tmax && o.f_exit != excl_face) { t_out = o.t_exit; return o.f_exit; }
     return -1;
 }
+template <bool NC = false>
 __device__ __forceinline__ int box_prim_hit(const GrtBox* bx, const RayD& r, float tmin, float tmax, int excl_face, float& t_out, bool& near_tmin) {
     BoxSlab o;
     near_tmin = false;
-    if (!box_prim_slab(bx, r, o)) return -1;
+    if (!box_prim_slab<NC>(bx, r, o)) return -1;
     return box_prim_pick(o, tmin, tmax, excl_face, t_out, near_tmin);
 }
 
 // ---- Triangle.Hit (Möller–Trumbore), objects.go:408-461 --------------------
-__device__ __forceinline__ bool tri_hit(const GrtTri* tp, const RayD& r, float tmin, float tmax, uint32_t self_id, float& t_out, float& u_out, float& v_out) {
+// The same test on the fp64 vertices, in the reference's expression order (objects.go:409-433): used by the ray-query
+// kernel when an fp32 barycentric lies within fp32 error of an edge (see tri_hit).
+static __device__ __noinline__ bool tri_hit_f64(const double* v, f3 o32, f3 d32, float tmin, float tmax, float& t_out, float& u_out, float& v_out) {
+    const d3 v0 = ldd3(v), e0 = ldd3(v + 3) - v0, e1 = ldd3(v + 6) - v0;
+    const d3 o = tod3(o32), d = tod3(d32);
+    const d3 pvec = cross(d, e1);
+    const double det = dot(e0, pvec);
+    if (fabs(det) < 1e-8) return false;
+    const double invDet = 1.0 / det;
+    const d3 tvec = o - v0;
+    const double u = dot(tvec, pvec) * invDet;
+    if (u < 0 || u > 1) return false;
+    const d3 qvec = cross(tvec, e0);
+    const double vv = dot(d, qvec) * invDet;
+    if (vv < 0 || (u + vv) > 1) return false;
+    const double tl = dot(e1, qvec) * invDet;
+    if (tl < (double)tmin || tl > (double)tmax) return false;
+    t_out = (float)tl; u_out = (float)u; v_out = (float)vv;
+    return true;
+}
+
+// EDGE64 (the C-ABI ray query, F_TMIN_F64 builds): an fp32 barycentric within 2e-3 of an edge — one fp32 ulp of a
+// vertex 20 units from the origin is 3e-5 of an edge of the 1M-triangle mesh, more for a grazing ray — is decided on the
+// fp64 vertices like the reference does, so that the hit id on a shared edge is the reference's.  The integrator keeps
+// the fp32 decision: either neighbour of a shared edge is the same surface point.
+template <bool EDGE64 = false>
+__device__ __forceinline__ bool tri_hit(const GrtTri* tp, const double* v64, const RayD& r, float tmin, float tmax, uint32_t self_id, float& t_out, float& u_out, float& v_out) {
     const float4 a = __ldg((const float4*)tp);        // v0, mat
     const float4 b = __ldg((const float4*)tp + 1);    // e0, id
     const float4 c = __ldg((const float4*)tp + 2);    // e1, flags
@@ -336,10 +400,15 @@ __device__ __forceinline__ bool tri_hit(const GrtTri* tp, const RayD& r, float t
     float invDet = 1.0f / det;
     f3 tvec = r.o - mk3(a.x, a.y, a.z);
     float u = dot(tvec, pvec) * invDet;
-    if (u < 0 || u > 1) return false;
+    const float E = EDGE64 ? 2e-3f : 0.0f;
+    if (u < -E || u > 1 + E) return false;
     f3 qvec = cross(tvec, e0);
     float v = dot(r.d, qvec) * invDet;
-    if (v < 0 || (u + v) > 1) return false;
+    if (v < -E || (u + v) > 1 + E) return false;
+    if (EDGE64) {
+        if (v64 && ((u < E) | (v < E) | (u + v > 1 - E))) return tri_hit_f64(v64, r.o, r.d, tmin, tmax, t_out, u_out, v_out);
+        if (u < 0 || u > 1 || v < 0 || (u + v) > 1) return false;
+    }
     float tl = dot(e1, qvec) * invDet;
     if (tl < tmin || tl > tmax) return false;
     t_out = tl; u_out = u; v_out = v;
@@ -357,7 +426,9 @@ __device__ __forceinline__ float tri_refine_t(const double* v, const RayD& r, fl
     return (float)(dot(e1, qvec) / det);
 }
 
-#define GRT_STACK_MAIN 48
+#ifndef GRT_STACK_MAIN
+#define GRT_STACK_MAIN 64
+#endif
 #define GRT_STACK_BOUNDARY 32
 
 // Context for the medium's random draw (medium.go:47): stream (pixel, sample,
@@ -379,10 +450,10 @@ struct MediumRngCtx {
 // STRIDE == 1: the stack is a thread-local array.  STRIDE > 1: the stack is this thread's column of a shared-memory
 // array [STACK][STRIDE] (`ext` points at row 0): a local-memory stack of 113 664 resident threads does not fit the
 // L1/L2, so every pop of a deep traversal was an L2 or DRAM round trip on the critical path.
-template <bool BOUNDARY, int STRIDE = 1>
+template <bool BOUNDARY, int STRIDE = 1, int NS = GRT_TRAV_SMEM>
 struct TravState {
     static constexpr int STACK = BOUNDARY ? GRT_STACK_BOUNDARY : GRT_STACK_MAIN;
-    static constexpr int NSMEM = STRIDE == 1 ? 0 : GRT_TRAV_SMEM;   // entries held in shared memory; deeper ones overflow
+    static constexpr int NSMEM = STRIDE == 1 ? 0 : NS;   // entries held in shared memory; deeper ones overflow
     uint32_t local[STACK - NSMEM > 0 ? STACK - NSMEM : 1];
     uint32_t* ext;
     __device__ __forceinline__ uint32_t& at(int i) { return (STRIDE == 1 || i >= NSMEM) ? local[i - NSMEM] : ext[i * STRIDE]; }
@@ -426,7 +497,7 @@ __device__ __forceinline__ bool trav_run(const SceneView& sv, TS& ts, const RayD
             auto one = [&](uint32_t k) {
                 float t, a, b;
                 bool unc;
-                bool ok = quad_hit(q + k, r, tmin, tmax, t, a, b, unc);
+                bool ok = quad_hit<GRT_PRIM_NC(FEAT)>(q + k, r, tmin, tmax, t, a, b, unc);
                 if ((FEAT & F_TMIN_F64) && (FEAT & F_ROTQUAD) && unc) ok = quad_hit_f64(q + k, sv.quads_cold() + idx + k, r, tmin, tmax, t, a, b);
                 // a planar primitive cannot be re-hit by a ray leaving it (the fp64 reference finds t ~ 1e-13 < tmin)
                 if (FEAT & F_DUPIDS) ok = ok && (sv.quads_cold()[idx + k].id != excl);
@@ -451,13 +522,15 @@ __device__ __forceinline__ bool trav_run(const SceneView& sv, TS& ts, const RayD
         if ((FEAT & F_BOX) && type == GRT_REF_BOX) {
             const GrtBox* bx = sv.boxes() + idx;
             if (STATS) tc->box += n;
+#pragma unroll 1   // (ptxas otherwise unrolls this by four: +120 instructions in the Cornell megakernel for runs of two boxes, -6 %)
             for (uint32_t k = 0; k < n; k++, bx++) {
-                const uint32_t qref = GRT_MAKE_REF(GRT_REF_QUAD, bx->first_quad);
+                const uint32_t first_quad = ldro<GRT_PRIM_NC(FEAT)>(&bx->first_quad);
+                const uint32_t qref = GRT_MAKE_REF(GRT_REF_QUAD, first_quad);
                 int excl_face = -1;
                 if (FEAT & F_DUPIDS) { for (int f = 0; f < 6; f++) if (sv.quads_cold()[bx->first_quad + f].id == excl) excl_face = f; }
                 else if (excl_ref - qref < 6u) excl_face = (int)(excl_ref - qref);
                 float t; bool near;
-                int face = box_prim_hit(bx, r, tmin, tmax, excl_face, t, near);
+                int face = box_prim_hit<GRT_PRIM_NC(FEAT)>(bx, r, tmin, tmax, excl_face, t, near);
                 if ((FEAT & F_TMIN_F64) && near) {
                     // a candidate within fp32 resolution of tmin: decide with the six quads (fp64 plane fallback inside)
                     const DQuadHot* q = sv.quads() + bx->first_quad;
@@ -476,7 +549,7 @@ __device__ __forceinline__ bool trav_run(const SceneView& sv, TS& ts, const RayD
             if (STATS) tc->sphere += n;
             for (uint32_t k = 0; k < n; k++, s++) {
                 float t;
-                if (sphere_hit(*s, r, tmin, tmax, s->id == excl, t)) { tmax = t; hit.ref = ref + k; hit.u = 0; hit.v = 0; }
+                if (sphere_hit<GRT_RAY_KEEPS_F64(FEAT), GRT_PRIM_NC(FEAT)>(*s, r, tmin, tmax, ldro<GRT_PRIM_NC(FEAT)>(&s->id) == excl, t)) { tmax = t; hit.ref = ref + k; hit.u = 0; hit.v = 0; }
             }
             return true;
         }
@@ -484,7 +557,9 @@ __device__ __forceinline__ bool trav_run(const SceneView& sv, TS& ts, const RayD
             if (STATS) tc->tri += n;
             for (uint32_t k = 0; k < n; k++) {
                 float t, u, v;
-                if (tri_hit(sv.ds->tris + idx + k, r, tmin, tmax, excl, t, u, v)) { tmax = t; hit.ref = ref + k; hit.u = u; hit.v = v; }
+                constexpr bool EDGE64 = (FEAT & F_TMIN_F64) != 0;
+                const double* v64 = (EDGE64 && sv.ds->tri_v64) ? sv.ds->tri_v64 + 9 * (size_t)(idx + k) : nullptr;
+                if (tri_hit<EDGE64>(sv.ds->tris + idx + k, v64, r, tmin, tmax, excl, t, u, v)) { tmax = t; hit.ref = ref + k; hit.u = u; hit.v = v; }
             }
             return true;
         }
@@ -531,14 +606,14 @@ __device__ __forceinline__ bool trav_run(const SceneView& sv, TS& ts, const RayD
             if ((FEAT & F_SPHERE) && btype == GRT_REF_SPHERE) {
                 if (STATS) tc->sphere += 2;
                 float nearr, farr;
-                if (!sphere_roots(sv.spheres()[bidx], r, false, nearr, farr)) return;
+                if (!sphere_roots<GRT_RAY_KEEPS_F64(FEAT), GRT_PRIM_NC(FEAT)>(sv.spheres()[bidx], r, false, nearr, farr)) return;
                 if (!sphere_pick(nearr, farr, -INF, INF, h1.t)) return;
                 if (!sphere_pick(nearr, farr, h1.t + 0.0001f, INF, h2.t)) return;
             } else if ((FEAT & F_BOX) && !(FEAT & F_TMIN_F64) && btype == GRT_REF_BOX) {
                 if (STATS) tc->box += 2;
                 BoxSlab bs;
                 bool nt;
-                if (!box_prim_slab(sv.boxes() + bidx, r, bs)) return;
+                if (!box_prim_slab<GRT_PRIM_NC(FEAT)>(sv.boxes() + bidx, r, bs)) return;
                 if (box_prim_pick(bs, -INF, INF, -1, h1.t, nt) < 0) return;
                 if (box_prim_pick(bs, h1.t + 0.0001f, INF, -1, h2.t, nt) < 0) return;
             } else {
@@ -564,10 +639,11 @@ __device__ __forceinline__ bool trav_run(const SceneView& sv, TS& ts, const RayD
     // order) becomes current and the other hit children wait on the stack, nearest on top
     auto node_step = [&](uint32_t& ref) -> bool {   // false: the stack ran dry
         const float4* np = nodes + GRT_WNODE_F4 * (ref & GRT_REF_MASK);
-        const float4 pnx = np[r.nx], pny = np[r.ny], pnz = np[r.nz];
-        const float4 pfx = np[3u - r.nx], pfy = np[5u - r.ny], pfz = np[7u - r.nz];
-        const uint4 ch = *(const uint4*)(np + 6);
-        const uint2 meta = *(const uint2*)(np + 7);
+        constexpr bool NC = GRT_NC_NODES != 0 && (FEAT & F_GMEM) != 0;   // 128-bit read-only (ld.global.nc) fetches unless the nodes sit in shared memory
+        const float4 pnx = ldro<NC>(np + r.nx), pny = ldro<NC>(np + r.ny), pnz = ldro<NC>(np + r.nz);
+        const float4 pfx = ldro<NC>(np + (3u - r.nx)), pfy = ldro<NC>(np + (5u - r.ny)), pfz = ldro<NC>(np + (7u - r.nz));
+        const uint4 ch = ldro<NC>((const uint4*)(np + 6));
+        const uint2 meta = ldro<NC>((const uint2*)(np + 7));
         if (STATS) tc->box += meta.y;
         const float INF = __int_as_float(0x7f800000);
         const bool ordered = (meta.x & 1u) != 0u;
@@ -718,7 +794,8 @@ __device__ __forceinline__ void finish_hit(const SceneView& sv, const RayD& r, c
         double cz = sp.c0[2] + (double)r.time * (double)sp.dc[2];
         double t = (double)h.t;
         double inv = 1.0 / sp.r;
-        f3 outward = mk3((float)((r.o64.x + t * r.d64.x - cx) * inv), (float)((r.o64.y + t * r.d64.y - cy) * inv), (float)((r.o64.z + t * r.d64.z - cz) * inv));
+        const d3 o64 = GRT_RAY_KEEPS_F64(FEAT) ? r.o64 : tod3(r.o), d64 = GRT_RAY_KEEPS_F64(FEAT) ? r.d64 : tod3(r.d);
+        f3 outward = mk3((float)((o64.x + t * d64.x - cx) * inv), (float)((o64.y + t * d64.y - cy) * inv), (float)((o64.z + t * d64.z - cz) * inv));
         set_face_normal(s, r.d, outward);
         if (want_sphere_uv) sphere_uv(sp, s);
         return;

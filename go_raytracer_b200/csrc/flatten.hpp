@@ -127,7 +127,8 @@ struct FlatScene {
 // their leaves in the reference's depth-first, left-first visiting order.
 struct FlattenOptions {
     int collapse_whole = 32;   // a BuildBVH result with at most this many leaves becomes one list
-    int collapse_leaf = 4;     // inside larger trees, subtrees with at most this many leaves become lists
+    int collapse_leaf = 1;     // inside larger trees, subtrees with at most this many leaves become lists (1: every primitive is its own leaf
+                               // and gets its own box in the 4-wide device BVH: measured best of 1/2/4/8, profiles/README.md round 2)
     bool box_prims = true;     // NewBox results are found with one slab test (GrtBox) instead of six quad tests
     bool order_hints = true;   // nodes carry the split axis so a ray may visit the nearer child first
     // BuildBVH's object order computed elsewhere (the GPU, grt_bvh_order) for lists of at least gpu_order_min

@@ -45,4 +45,5 @@ cudaError_t grt_dev_alloc(void** p, size_t bytes);
 void grt_dev_free(void* p);
 /* the wavefront variant's path pool (grown on demand, freed with the scene) and 64 pinned bytes for its counters */
 void* grt_internal_wf_pool(GrtSceneHandle h, size_t bytes, void** pinned64);
+void grt_internal_set_timing(const GrtTiming& t);
 int grt_make_dev_camera(const GrtCamera* c, grtd::DevCamera* out);

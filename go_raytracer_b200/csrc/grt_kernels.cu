@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(128) trace_batch_kernel(const __grid_constant_
     mr.pixel = (uint32_t)i; mr.sample = (uint32_t)(i >> 32); mr.bounce = 0; mr.k0 = 0; mr.k1 = 0; mr.count = 0;
     HitInfo h;
     GrtHit out;
-    if (closest_hit<FEAT | F_DUPIDS | F_TMIN_F64, false, false>(sv, ds.root, r, a.w, b.w, self_id, 0xFFFFFFFFu, &mr, h, nullptr)) {
+    if (closest_hit<FEAT | F_DUPIDS | F_TMIN_F64 | (STAGED == 0 ? F_GMEM : 0u), false, false>(sv, ds.root, r, a.w, b.w, self_id, 0xFFFFFFFFu, &mr, h, nullptr)) {
         Surface s;
         finish_hit<FEAT | F_TMIN_F64>(sv, r, h, true, s);
         out.t = h.t; out.id = s.id; out.ref = h.ref; out.front_face = s.front ? 1u : 0u;
@@ -297,14 +297,14 @@ __global__ void __launch_bounds__(GRT_MEGA_THREADS, mega_min_blocks(FEAT)) rende
             // the lanes that are done shade and start their next segment while the others resume (dev_trace.cuh)
             if (active && !tracing) { trav_begin(ts, P.scene.root, INF); tracing = true; med_count = 0; if (STATS) st_segments++; }
             mr.count = med_count;
-            const bool fin = trav_run<FEAT, false, STATS, true>(sv, ts, ray, 0.001f, self_id, self_ref, &mr, &tc, FULL, P.trav_exit16);
+            const bool fin = trav_run<FEAT | (STAGED == 0 ? F_GMEM : 0u), false, STATS, true>(sv, ts, ray, 0.001f, self_id, self_ref, &mr, &tc, FULL, P.trav_exit16);
             med_count = mr.count;
             if (!active || !fin) continue;
             tracing = false;
             hit = trav_end<FEAT>(sv, ts, ray, h);
         } else {
             if (STATS) st_segments++;
-            hit = closest_hit<FEAT, false, STATS>(sv, P.scene.root, ray, 0.001f, INF, self_id, self_ref, &mr, h, &tc);   // camera.go:300
+            hit = closest_hit<FEAT | (STAGED == 0 ? F_GMEM : 0u), false, STATS>(sv, P.scene.root, ray, 0.001f, INF, self_id, self_ref, &mr, h, &tc);   // camera.go:300
         }
 
         f3 Lterm = mk3(0, 0, 0);
@@ -550,14 +550,16 @@ static int repack_scene(const GrtScene* s, Repacked& R) {
         grt_set_error("scene needs a deeper traversal stack than the kernels provide");
         return GRT_E_UNSUPPORTED;
     }
+    // NODE refs held by list entries (list-only scenes have none; in BVH scenes the lists themselves became wide nodes
+    // and the entries are no longer referenced), by media and by the root now name wide nodes
     auto to_wide = [&](uint32_t ref) -> uint32_t {
         uint32_t flag = ref & GRT_LIST_LAST, r = ref & ~GRT_LIST_LAST;
         if (GRT_REF_TYPE(r) == GRT_REF_NODE) r = GRT_MAKE_REF(GRT_REF_NODE, R.wide.node_map[r & GRT_REF_MASK]);
         return r | flag;
     };
     for (size_t k = 0; k < entries.size(); k += 2) entries[k] = to_wide(entries[k]);
-    for (auto& m : R.media) m.boundary = to_wide(m.boundary);
-    R.root = to_wide(remap(s->root));
+    for (size_t i = 0; i < R.media.size(); i++) R.media[i].boundary = R.wide.media_boundary[i];
+    R.root = R.wide.root;
     return GRT_OK;
 }
 
@@ -883,12 +885,27 @@ extern "C" int grt_render_device(GrtSceneHandle h, const GrtCamera* cam, const G
     CUDA_TRY(cudaMemsetAsync(h->d_counter, 0, 4, st));
     bool stats = (opt->flags & GRT_OPT_STATS) && d_stats;
     uint32_t f = h->ds.features | (cam->defocus_angle > 0 ? F_DEFOCUS : 0u);
-    if ((f & ~V_CORNELL) == 0) return launch_mega<V_CORNELL>(h, P, stats, st);
-    if ((f & ~V_SMOKE) == 0) return launch_mega<V_SMOKE>(h, P, stats, st);
-    if ((f & ~V_SPHERES) == 0) return launch_mega<V_SPHERES>(h, P, stats, st);
-    if ((f & ~V_MESH) == 0) return launch_mega<V_MESH>(h, P, stats, st);
-    if ((f & ~V_FULL_UNIQ) == 0) return launch_mega<V_FULL_UNIQ>(h, P, stats, st);
-    return launch_mega<V_FULL>(h, P, stats, st);
+    const bool timing = (opt->flags & GRT_OPT_TIMING) != 0;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    if (timing) { CUDA_TRY(cudaEventCreate(&t0)); CUDA_TRY(cudaEventCreate(&t1)); CUDA_TRY(cudaEventRecord(t0, st)); }
+    if ((f & ~V_CORNELL) == 0) rc = launch_mega<V_CORNELL>(h, P, stats, st);
+    else if ((f & ~V_SMOKE) == 0) rc = launch_mega<V_SMOKE>(h, P, stats, st);
+    else if ((f & ~V_SPHERES) == 0) rc = launch_mega<V_SPHERES>(h, P, stats, st);
+    else if ((f & ~V_MESH) == 0) rc = launch_mega<V_MESH>(h, P, stats, st);
+    else if ((f & ~V_FULL_UNIQ) == 0) rc = launch_mega<V_FULL_UNIQ>(h, P, stats, st);
+    else rc = launch_mega<V_FULL>(h, P, stats, st);
+    if (timing) {
+        if (!rc) {
+            GrtTiming T;
+            memset(&T, 0, sizeof(T));
+            float ms = 0;
+            if (cudaEventRecord(t1, st) == cudaSuccess && cudaEventSynchronize(t1) == cudaSuccess) cudaEventElapsedTime(&ms, t0, t1);
+            T.total_ms = T.extend_ms = ms; T.extend_launches = T.launches = 1;
+            grt_internal_set_timing(T);
+        }
+        cudaEventDestroy(t0); cudaEventDestroy(t1);
+    }
+    return rc;
 }
 
 extern "C" int grt_tonemap_device(const float* d_rgb_sum, uint8_t* d_rgb8, uint64_t n_values, float scale, void* stream) {

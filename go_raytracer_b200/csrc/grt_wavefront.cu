@@ -20,6 +20,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string>
+#include <vector>
 #include "dev_shade.cuh"
 #include "grt_internal.h"
 
@@ -90,10 +91,19 @@ __global__ void __launch_bounds__(256) wf_generate(const __grid_constant__ WfPar
 #ifndef WF_EXT_MIN_BLOCKS
 #define WF_EXT_MIN_BLOCKS 4   /* 64 registers, 32 warps/SM: best of 3/4/5 on the book scenes (C4 342 / 385 / 340 Mpaths/s) */
 #endif
+// BVH scenes keep the first WF_EXT_SMEM traversal-stack entries of every thread in shared memory (one column per
+// thread, conflict-free): as a local array every push / pop was an LDL / STL through the L1 (7 % of this kernel's
+// instructions on the book-2 cover, ncu round 1) next to the node and primitive fetches it competes with.
+#ifndef WF_EXT_SMEM
+#define WF_EXT_SMEM 16
+#endif
 template <uint32_t FEAT, int STAGED>
 __global__ void __launch_bounds__(256, WF_EXT_MIN_BLOCKS) wf_extend(const __grid_constant__ WfParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
     SceneView sv = wf_view<STAGED>(P, smem);
+    constexpr bool BVH = (FEAT & F_NODE) != 0;
+    constexpr uint32_t TF = FEAT | (STAGED == 0 ? F_GMEM : 0u);
+    __shared__ uint32_t trav_smem[BVH ? WF_EXT_SMEM : 1][BVH ? 256 : 1];
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned FULL = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31u;
@@ -108,7 +118,11 @@ __global__ void __launch_bounds__(256, WF_EXT_MIN_BLOCKS) wf_extend(const __grid
             mr.pixel = s3.x; mr.sample = s3.y; mr.bounce = s3.z & 255u; mr.k0 = P.k0; mr.k1 = P.k1; mr.count = 0;
             HitInfo h;
             const float INF = __int_as_float(0x7f800000);
-            bool hit = closest_hit<FEAT, false, false>(sv, P.scene.root, ray, 0.001f, INF, s3.w, __float_as_uint(s1.w), &mr, h, nullptr);
+            TravState<false, BVH ? 256 : 1, WF_EXT_SMEM> ts;
+            ts.ext = &trav_smem[0][BVH ? threadIdx.x : 0];
+            trav_begin(ts, P.scene.root, INF);
+            trav_run<TF, false, false, false>(sv, ts, ray, 0.001f, s3.w, __float_as_uint(s1.w), &mr, nullptr, 0u, 0);
+            const bool hit = trav_end<FEAT>(sv, ts, ray, h);
             if (!hit) { h.t = INF; h.ref = GRT_MAKE_REF(GRT_REF_NONE, 0); h.u = h.v = 0; q = Q_TERMINAL; }
             else {
                 uint32_t type = GRT_REF_TYPE(h.ref), idx = h.ref & GRT_REF_MASK, mat;
@@ -147,12 +161,13 @@ __global__ void __launch_bounds__(256, WF_EXT_MIN_BLOCKS) wf_extend(const __grid
 // unlike the megakernel nothing ties a lane to a pixel.
 #define WF_DYN_THREADS 128
 #ifndef WF_DYN_MIN_BLOCKS
-#define WF_DYN_MIN_BLOCKS 8   /* 64 registers, 32 warps/SM: measured best of 6/8/10 (271 / 295 / 267 Mpaths/s on the 1M-triangle mesh) */
+#define WF_DYN_MIN_BLOCKS 7   /* 72 registers, 28 warps/SM: measured best of 6/7/8 with the 4-wide BVH (430 / 462 / 442 Mpaths/s on the 1M-triangle mesh) */
 #endif
 template <uint32_t FEAT, int STAGED>
 __global__ void __launch_bounds__(WF_DYN_THREADS, WF_DYN_MIN_BLOCKS) wf_extend_dyn(const __grid_constant__ WfParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
     SceneView sv = wf_view<STAGED>(P, smem);
+    constexpr uint32_t TF = FEAT | (STAGED == 0 ? F_GMEM : 0u);
     __shared__ uint32_t trav_smem[GRT_TRAV_SMEM][WF_DYN_THREADS];
     TravState<false, WF_DYN_THREADS> ts;
     ts.ext = &trav_smem[0][threadIdx.x];
@@ -193,7 +208,7 @@ __global__ void __launch_bounds__(WF_DYN_THREADS, WF_DYN_MIN_BLOCKS) wf_extend_d
         if (!__any_sync(FULL, have)) { if (exhausted) break; else continue; }
         MediumRngCtx mr;
         mr.pixel = s3.x; mr.sample = s3.y; mr.bounce = s3.z & 255u; mr.k0 = P.k0; mr.k1 = P.k1; mr.count = med_count;
-        const bool fin = trav_run<FEAT, false, false, true>(sv, ts, ray, 0.001f, s3.w, self_ref, &mr, nullptr, FULL, P.exit16);
+        const bool fin = trav_run<TF, false, false, true>(sv, ts, ray, 0.001f, s3.w, self_ref, &mr, nullptr, FULL, P.exit16);
         med_count = mr.count;
         int q = -1;
         if (have && fin) {
@@ -303,6 +318,14 @@ __global__ void wf_init_slots(uint4* S3, uint32_t P) {
 }
 
 // ---- host driver ---------------------------------------------------------------------------------------
+static thread_local GrtTiming g_timing;
+extern "C" int grt_last_timing(GrtTiming* out) {
+    if (!out) { grt_set_error("grt_last_timing: NULL argument"); return GRT_E_INVALID; }
+    *out = g_timing;
+    return GRT_OK;
+}
+void grt_internal_set_timing(const GrtTiming& t) { g_timing = t; }
+
 #define CU(call)                                                                                         \
     do {                                                                                                 \
         cudaError_t e_ = (call);                                                                         \
@@ -310,13 +333,14 @@ __global__ void wf_init_slots(uint4* S3, uint32_t P) {
     } while (0)
 
 template <uint32_t FEAT>
-static int wf_run(GrtSceneHandle h, WfParams& P, cudaStream_t st, uint32_t* h_counters) {
+static int wf_run(GrtSceneHandle h, WfParams& P, cudaStream_t st, uint32_t* h_counters, bool timing) {
     int rc = GRT_OK;
-    // Triangle meshes: persistent extend with dynamic ray fetch (166 -> 271 Mpaths/s on the 1M-triangle config).  The
-    // sphere / box BVHs of the book scenes have short, even traversals and expensive leaves; the plain
-    // one-thread-per-slot extend is faster there (311 vs 252 and 720 vs 633 Mpaths/s; profiles/README.md).
+    // Persistent extend with dynamic ray fetch (wf_extend_dyn) vs one thread per slot (wf_extend), measured with the 4-wide
+    // BVH (profiles/README.md, round 2): triangle meshes 462 vs 232 Mpaths/s, the sphere BVH of book 1 796 vs 696; the
+    // book-2 cover (spheres + boxes + two media under one top-level list) 399 vs 458 — its rays alternate between node
+    // walks, fp64 sphere tests, box slabs and medium draws, and lock-step voting only adds waiting there.
     constexpr bool can_dyn = (FEAT & F_NODE) != 0;
-    bool dyn = can_dyn && (FEAT & F_TRI) != 0 && P.scene.n_tris >= 1024u;
+    bool dyn = can_dyn && (((FEAT & F_TRI) != 0 && P.scene.n_tris >= 1024u) || FEAT == (V_SPHERES));
     if (const char* e = getenv("GRT_WF_DYN")) dyn = can_dyn && (atoi(e) == 2 || (dyn && atoi(e) != 0));   // 0: never, 2: whenever compiled in
     const bool staged = grt_internal_staged(h) == 2 && !dyn;   // whole-blob staging or none
     const unsigned dyn_blocks = (unsigned)grt_internal_sm_count(h) * WF_DYN_MIN_BLOCKS;
@@ -331,29 +355,41 @@ static int wf_run(GrtSceneHandle h, WfParams& P, cudaStream_t st, uint32_t* h_co
         cudaFuncSetAttribute(wf_shade<FEAT, 2, Q_SPECULAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     }
     // one bounce: reset the queue counters, refill free slots, extend, shade the three queues
+    std::vector<cudaEvent_t> tev;   // GRT_OPT_TIMING: four events per bounce (before generate / extend / shade, after shade)
+    auto mark = [&](cudaStream_t s_) {
+        if (!timing) return;
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreate(&e) == cudaSuccess) { cudaEventRecord(e, s_); tev.push_back(e); }
+    };
     auto one_iteration = [&](cudaStream_t s_) -> cudaError_t {
         cudaError_t e = cudaMemsetAsync(P.counters, 0, C_WORDS * 4, s_);
         if (e != cudaSuccess) return e;
+        mark(s_);
         wf_generate<FEAT><<<blocks, 256, 0, s_>>>(P);
+        mark(s_);
         if (dyn) {
             if constexpr (can_dyn) {
                 // the scene is read from global memory (L1/L2): the shared memory holds the traversal stacks
                 wf_extend_dyn<FEAT, 0><<<dyn_blocks, WF_DYN_THREADS, 0, s_>>>(P);
+                mark(s_);
                 wf_shade<FEAT, 0, Q_TERMINAL><<<blocks, 256, 0, s_>>>(P);
                 wf_shade<FEAT, 0, Q_DIFFUSE><<<blocks, 256, 0, s_>>>(P);
                 if (has_spec) wf_shade<FEAT, 0, Q_SPECULAR><<<blocks, 256, 0, s_>>>(P);
             }
         } else if (staged) {
             wf_extend<FEAT, 2><<<blocks, 256, smem, s_>>>(P);
+            mark(s_);
             wf_shade<FEAT, 2, Q_TERMINAL><<<blocks, 256, smem, s_>>>(P);
             wf_shade<FEAT, 2, Q_DIFFUSE><<<blocks, 256, smem, s_>>>(P);
             if (has_spec) wf_shade<FEAT, 2, Q_SPECULAR><<<blocks, 256, smem, s_>>>(P);
         } else {
             wf_extend<FEAT, 0><<<blocks, 256, 0, s_>>>(P);
+            mark(s_);
             wf_shade<FEAT, 0, Q_TERMINAL><<<blocks, 256, 0, s_>>>(P);
             wf_shade<FEAT, 0, Q_DIFFUSE><<<blocks, 256, 0, s_>>>(P);
             if (has_spec) wf_shade<FEAT, 0, Q_SPECULAR><<<blocks, 256, 0, s_>>>(P);
         }
+        mark(s_);
         return cudaSuccess;
     };
     const uint64_t per_iter = has_spec ? 5 : 4;
@@ -363,7 +399,8 @@ static int wf_run(GrtSceneHandle h, WfParams& P, cudaStream_t st, uint32_t* h_co
     // a private stream ordered after, and waited for by, the caller's stream.  GRT_WF_GRAPH=0: plain launches.
     // (Measured: +0.5 % — the launches were already hidden behind the running kernels; kept because it removes 47 of
     // every 48 host calls from the render thread.)
-    static const bool use_graph = [] { const char* e = getenv("GRT_WF_GRAPH"); return !(e && atoi(e) == 0); }();
+    static const bool graph_env = [] { const char* e = getenv("GRT_WF_GRAPH"); return !(e && atoi(e) == 0); }();
+    const bool use_graph = graph_env && !timing;   // events inside a captured graph cannot be read back: plain launches when timing
     cudaStream_t ws = nullptr;
     cudaEvent_t e_in = nullptr, e_out = nullptr;
     cudaGraph_t graph = nullptr;
@@ -410,7 +447,24 @@ static int wf_run(GrtSceneHandle h, WfParams& P, cudaStream_t st, uint32_t* h_co
         }
     }
     CU(cudaGetLastError());
+    if (timing) {
+        CU(cudaStreamSynchronize(st));
+        GrtTiming T;
+        memset(&T, 0, sizeof(T));
+        for (size_t k = 0; k + 3 < tev.size(); k += 4) {
+            float a = 0, b = 0, c = 0;
+            cudaEventElapsedTime(&a, tev[k], tev[k + 1]);
+            cudaEventElapsedTime(&b, tev[k + 1], tev[k + 2]);
+            cudaEventElapsedTime(&c, tev[k + 2], tev[k + 3]);
+            T.generate_ms += a; T.extend_ms += b; T.shade_ms += c;
+            T.extend_launches++;
+        }
+        if (tev.size() >= 4) { float t = 0; cudaEventElapsedTime(&t, tev.front(), tev.back()); T.total_ms = t; }
+        T.launches = launches;
+        grt_internal_set_timing(T);
+    }
 done:
+    for (cudaEvent_t e : tev) cudaEventDestroy(e);
     if (exec) cudaGraphExecDestroy(exec);
     if (graph) cudaGraphDestroy(graph);
     if (e_in) cudaEventDestroy(e_in);
@@ -450,6 +504,7 @@ int grt_render_wavefront(GrtSceneHandle h, const GrtCamera* cam, const GrtOption
     if (const char* e = getenv("GRT_WF_EXIT16")) { int v = atoi(e); if (v >= 0 && v <= 16) P.exit16 = v; }
     void* pool = nullptr;
     uint32_t* h_counters = nullptr;
+    const bool timing = (opt->flags & GRT_OPT_TIMING) != 0;
     const bool trace = getenv("GRT_WF_TRACE") != nullptr;
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     double t_a = now(), t_b = 0, t_c = 0;
@@ -473,12 +528,12 @@ int grt_render_wavefront(GrtSceneHandle h, const GrtCamera* cam, const GrtOption
     {
         uint32_t f = (P.scene.features & ~F_DUPIDS) | (cam->defocus_angle > 0 ? F_DEFOCUS : 0u);
         bool dup = (P.scene.features & F_DUPIDS) != 0;
-        if (!dup && (f & ~V_CORNELL) == 0) rc = wf_run<V_CORNELL>(h, P, st, h_counters);
-        else if (!dup && (f & ~V_SMOKE) == 0) rc = wf_run<V_SMOKE>(h, P, st, h_counters);
-        else if (!dup && (f & ~V_SPHERES) == 0) rc = wf_run<V_SPHERES>(h, P, st, h_counters);
-        else if (!dup && (f & ~V_MESH) == 0) rc = wf_run<V_MESH>(h, P, st, h_counters);
-        else if (!dup) rc = wf_run<V_FULL_UNIQ>(h, P, st, h_counters);
-        else rc = wf_run<F_ALL>(h, P, st, h_counters);
+        if (!dup && (f & ~V_CORNELL) == 0) rc = wf_run<V_CORNELL>(h, P, st, h_counters, timing);
+        else if (!dup && (f & ~V_SMOKE) == 0) rc = wf_run<V_SMOKE>(h, P, st, h_counters, timing);
+        else if (!dup && (f & ~V_SPHERES) == 0) rc = wf_run<V_SPHERES>(h, P, st, h_counters, timing);
+        else if (!dup && (f & ~V_MESH) == 0) rc = wf_run<V_MESH>(h, P, st, h_counters, timing);
+        else if (!dup) rc = wf_run<V_FULL_UNIQ>(h, P, st, h_counters, timing);
+        else rc = wf_run<F_ALL>(h, P, st, h_counters, timing);
     }
 done:
     if (pool) { cudaStreamSynchronize(st); t_c = now(); }   // the pool stays with the scene handle

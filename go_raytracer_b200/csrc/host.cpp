@@ -1,4 +1,5 @@
 // host.cpp — C API over the host-side mirror (include/grt_host.h).
+#include "jpeg_go.hpp"
 #include "../../include/grt_host.h"
 #include "scene_ir.hpp"
 #include "scenes.hpp"
@@ -44,6 +45,20 @@ int grt_host_checkerboard(GrtHostScene* s, double scale, int even_tex, int odd_t
 int grt_host_image(GrtHostScene* s, int w, int h, const uint8_t* rgb) {
     if (w <= 0 || h <= 0 || !rgb) return fail("bad image");
     GUARD(s->ir.AddImage(w, h, rgb));
+}
+// imageLoader.LoadImage (imageLoader.go:28-47) for JPEG files: Go's image/jpeg + color.YCbCr arithmetic (jpeg_go.hpp), so
+// the texels are the ones the reference renders with.  Two calls: rgb == NULL reports the size, then with a buffer.
+int grt_host_decode_jpeg(const uint8_t* data, size_t n, int* width, int* height, uint8_t* rgb, size_t cap) {
+    if (!data || !width || !height) return fail("grt_host_decode_jpeg: NULL argument");
+    grt::jpeg::Image img;
+    std::string err = grt::jpeg::decode(data, n, img);
+    if (!err.empty()) return fail("jpeg: " + err);
+    *width = img.width; *height = img.height;
+    if (rgb) {
+        if (cap < img.rgb.size()) return fail("grt_host_decode_jpeg: buffer too small");
+        memcpy(rgb, img.rgb.data(), img.rgb.size());
+    }
+    return 0;
 }
 int grt_host_image_texture(GrtHostScene* s, int image) {
     if (image < 0 || image >= (int)s->ir.images.size()) return fail("bad image id");

@@ -202,7 +202,7 @@ inline std::string decode(const uint8_t* data, size_t n, Image& out) {
     size_t pos = 2;
     bool done = false, saw_scan = false;
     while (!done) {
-        if (pos + 4 > n) return "truncated before EOI";
+        if (pos + 2 > n) return "truncated before EOI";
         if (data[pos] != 0xFF) return "expected a marker";
         while (pos < n && data[pos] == 0xFF) pos++;   // fill bytes
         if (pos >= n) return "truncated";

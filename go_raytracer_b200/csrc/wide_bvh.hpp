@@ -22,10 +22,12 @@
 // top of the tree: that prefix is what the kernels stage in shared memory.
 #pragma once
 #include <stdint.h>
+#include <stdlib.h>
 #include <math.h>
 #include <string.h>
 #include <algorithm>
 #include <deque>
+#include <functional>
 #include <limits>
 #include <string>
 #include <vector>
@@ -60,6 +62,9 @@ struct Box {
 struct Result {
     std::vector<float> wnodes;         // GRT_WNODE_FLOATS per node
     std::vector<uint32_t> node_map;    // binary node index -> wide node index (0xFFFFFFFF: absorbed into its parent)
+    std::vector<uint32_t> list_map;    // list entry index -> wide node index of the list that starts there (0xFFFFFFFF: none)
+    std::vector<uint32_t> media_boundary;   // device ref of every medium's boundary
+    uint32_t root = 0;                 // device ref of the world
     uint32_t n_wide = 0;
     int need_main = 0, need_boundary = 0;   // traversal stack entries a closest-hit query can hold at once
     std::string error;
@@ -73,42 +78,140 @@ class Builder {
 
     bool run(uint32_t root, Result& R) {
         const uint32_t NONE_IDX = 0xFFFFFFFFu;
+        Rp = &R;
         R.node_map.assign(N.size(), NONE_IDX);
+        R.list_map.assign(E.size() / 2, NONE_IDX);
         hasMedium.assign(N.size(), -1);
-        std::deque<uint32_t> queue;
-        auto enqueue = [&](uint32_t b) -> uint32_t {
-            if (R.node_map[b] == NONE_IDX) { R.node_map[b] = R.n_wide++; queue.push_back(b); }
-            return R.node_map[b];
+        // height of every binary subtree (the flattener emits parents before children: one reverse pass)
+        height.assign(N.size(), 0);
+        for (size_t b = N.size(); b-- > 0;) {
+            int hgt = 0;
+            const uint32_t c[2] = {N[b].left & ~GRT_NODE_HINT_BIT, N[b].right & ~GRT_NODE_HINT_BIT};
+            for (int k = 0; k < 2; k++) if (type(c[k]) == GRT_REF_NODE && idx(c[k]) < N.size()) hgt = std::max(hgt, (idx(c[k]) > b ? height[idx(c[k])] : 0) + 1);
+            height[b] = hgt;
+        }
+        // HittableLists become wide nodes too when the scene has a BVH at all (list-only scenes — the Cornell boxes —
+        // keep their ordered runs and never compile the node code): every item gets its own box, a list without a
+        // medium is visited nearest first, one with a medium in list order (hittable.go:129-136).
+        wideLists = !N.empty() && !(getenv("GRT_WIDE_LISTS") && atoi(getenv("GRT_WIDE_LISTS")) == 0);   // (env: A/B knob)
+        // work items: a binary node to collapse, or a consecutive range of a list's items to group
+        struct Work { bool list; uint32_t w, b; std::vector<uint32_t> items; };   // w: wide index to fill; b: binary node
+        std::deque<Work> queue;
+        auto alloc = [&]() -> uint32_t {
+            uint32_t w = R.n_wide++;
+            R.wnodes.resize((size_t)R.n_wide * GRT_WNODE_FLOATS, 0.0f);
+            return w;
         };
-        // roots: every NODE ref held outside the node array
-        if (type(root) == GRT_REF_NODE) enqueue(idx(root));
-        for (size_t k = 0; k + 1 < E.size(); k += 2) { uint32_t r = E[k] & ~GRT_LIST_LAST; if (type(r) == GRT_REF_NODE) enqueue(idx(r)); }
-        for (const GrtMedium& m : M) if (type(m.boundary) == GRT_REF_NODE) enqueue(idx(m.boundary));
+        std::function<uint32_t(uint32_t)> deviceRef = [&](uint32_t r) -> uint32_t {   // a remapped ABI ref as the device sees it
+            if (type(r) == GRT_REF_NODE) {
+                uint32_t b = idx(r);
+                if (R.node_map[b] == NONE_IDX) { R.node_map[b] = alloc(); queue.push_back(Work{false, R.node_map[b], b, {}}); }
+                return GRT_MAKE_REF(GRT_REF_NODE, R.node_map[b]);
+            }
+            if (type(r) == GRT_REF_LIST && wideLists) {
+                uint32_t e0 = idx(r);
+                if (R.list_map[e0] == NONE_IDX) {
+                    std::vector<uint32_t> items;
+                    listItems(e0, items);
+                    if (items.empty()) return GRT_MAKE_REF(GRT_REF_NONE, 0);
+                    if (items.size() == 1 && (items[0] & GRT_DREF_RUN_BIT)) return items[0];   // a list that is one short run
+                    R.list_map[e0] = alloc();
+                    queue.push_back(Work{true, R.list_map[e0], 0, std::move(items)});
+                }
+                return GRT_MAKE_REF(GRT_REF_NODE, R.list_map[e0]);
+            }
+            if (type(r) == GRT_REF_LIST) {   // a list kept as a list: the nodes it names still have to be built
+                for (uint32_t k = idx(r);; k++) {
+                    const uint32_t e = E[2 * k], first = e & ~GRT_LIST_LAST;
+                    if (type(first) == GRT_REF_NODE || type(first) == GRT_REF_LIST) deviceRef(first);
+                    if (e & GRT_LIST_LAST) break;
+                }
+                return r;
+            }
+            // run refs are decoded by the node code only: list-only scenes keep plain refs
+            return wideLists ? asRun(r) : r;
+        };
+        R.root = deviceRef(root);
+        R.media_boundary.clear();
+        // a medium whose boundary is a single primitive keeps the plain ref: the device solves it directly (dev_trace.cuh)
+        for (const GrtMedium& m : M) R.media_boundary.push_back(isPrim(type(m.boundary)) ? m.boundary : deviceRef(m.boundary));
         std::vector<uint32_t> kids;
         while (!queue.empty()) {
-            const uint32_t b = queue.front();
+            Work wk = std::move(queue.front());
             queue.pop_front();
-            const uint32_t w = R.node_map[b];
-            if (R.wnodes.size() < (size_t)(w + 1) * GRT_WNODE_FLOATS) R.wnodes.resize((size_t)(w + 1) * GRT_WNODE_FLOATS, 0.0f);
+            bool ordered;
+            const uint32_t w = wk.w;
             kids.clear();
-            pushChildren(kids, b);
-            // open the child with the largest box until there are four (children keep their left-to-right order)
-            while (kids.size() < 4) {
-                int best = -1;
-                double bestArea = -1.0;
-                for (size_t i = 0; i < kids.size(); i++) {
-                    if (type(kids[i]) != GRT_REF_NODE) continue;
+            std::vector<Box> kbox;
+            std::vector<uint32_t> kref;
+            if (!wk.list) {
+                const uint32_t b = wk.b;
+                pushChildren(kids, b);
+                // open the child with the largest box (the surface-area heuristic's choice) among the children whose
+                // subtree is within two levels of the tallest, until there are four; children keep their left-to-right
+                // order.  Opening by area alone can leave the deepest branch one binary level per wide level (a 2^20-leaf
+                // tree: 20 wide levels x 3 waiting siblings overflows the traversal stack); by height alone it ignores
+                // the boxes (-7 % on the 1M-triangle mesh).
+                while (kids.size() < 4) {
+                    int best = -1;
+                    double bestKey = -1.0;
+                    int maxH = -1;
+                    for (size_t i = 0; i < kids.size(); i++) if (type(kids[i]) == GRT_REF_NODE) maxH = std::max(maxH, height[idx(kids[i])]);
+                    // near the leaves (subtrees of height <= bottomH) the tallest child is opened instead, which packs four
+                    // leaves per node where area order would strand pairs
+                    const bool byHeight = mode == 1 || (mode == 2 && maxH <= bottomH);
+                    for (int pass = 0; pass < 2 && best < 0; pass++)   // second pass: no tall candidate fits, take any that does
+                        for (size_t i = 0; i < kids.size(); i++) {
+                            if (type(kids[i]) != GRT_REF_NODE || (pass == 0 && height[idx(kids[i])] < maxH - 2)) continue;
+                            std::vector<uint32_t> sub;
+                            pushChildren(sub, idx(kids[i]));
+                            if (kids.size() - 1 + sub.size() > 4) continue;
+                            const double a = nodeBox(idx(kids[i])).area();
+                            const double key = byHeight ? (double)height[idx(kids[i])] + a / (1.0 + a) * 0.5 : a;
+                            if (key > bestKey) { bestKey = key; best = (int)i; }
+                        }
+                    if (best < 0) break;
                     std::vector<uint32_t> sub;
-                    pushChildren(sub, idx(kids[i]));
-                    if (kids.size() - 1 + sub.size() > 4) continue;
-                    double a = nodeBox(idx(kids[i])).area();
-                    if (a > bestArea) { bestArea = a; best = (int)i; }
+                    pushChildren(sub, idx(kids[best]));
+                    kids.erase(kids.begin() + best);
+                    kids.insert(kids.begin() + best, sub.begin(), sub.end());
                 }
-                if (best < 0) break;
-                std::vector<uint32_t> sub;
-                pushChildren(sub, idx(kids[best]));
-                kids.erase(kids.begin() + best);
-                kids.insert(kids.begin() + best, sub.begin(), sub.end());
+                ordered = !subtreeHasMedium(GRT_MAKE_REF(GRT_REF_NODE, b));
+                for (uint32_t c : kids) {
+                    if (type(c) == GRT_REF_NONE) continue;
+                    Box bx;
+                    if (type(c) == GRT_REF_NODE) {
+                        // the ABI's node boxes are the fp64 geometry rounded outwards; the fp32 primitives the device tests
+                        // (v0, e0, e1 rounded separately) can sit an ulp OF THE LARGEST COORDINATE outside of them
+                        bx = nodeBox(idx(c));
+                        grow(bx, 5e-7);
+                    } else bx = refBox(c);
+                    if (bx.empty()) continue;    // nothing below this child can be hit
+                    kbox.push_back(bx);
+                    kref.push_back(deviceRef(c));
+                }
+            } else {
+                // a range of list items: up to four go straight into the node, more are split into four consecutive groups
+                std::vector<uint32_t>& items = wk.items;
+                ordered = true;
+                for (uint32_t it : items) if (subtreeHasMedium(it)) ordered = false;
+                const size_t n = items.size(), groups = n <= 4 ? n : 4;
+                size_t at = 0;
+                for (size_t gi = 0; gi < groups; gi++) {
+                    const size_t cnt = (n - at + (groups - gi) - 1) / (groups - gi);
+                    std::vector<uint32_t> sub(items.begin() + at, items.begin() + at + cnt);
+                    at += cnt;
+                    Box bx = Box::none();
+                    for (uint32_t it : sub) bx.add(itemBox(it));
+                    if (bx.empty()) continue;
+                    if (cnt == 1) kref.push_back((sub[0] & GRT_DREF_RUN_BIT) ? sub[0] : deviceRef(sub[0]));
+                    else {
+                        uint32_t cw = alloc();
+                        queue.push_back(Work{true, cw, 0, std::move(sub)});
+                        kref.push_back(GRT_MAKE_REF(GRT_REF_NODE, cw));
+                    }
+                    kbox.push_back(bx);
+                }
             }
             // write the node
             float* d = R.wnodes.data() + (size_t)w * GRT_WNODE_FLOATS;
@@ -118,23 +221,11 @@ class Builder {
                 for (int a = 0; a < 3; a++) { d[4 * a + k] = INF; d[12 + 4 * a + k] = -INF; }
                 refs[k] = GRT_MAKE_REF(GRT_REF_NONE, 0);
             }
-            bool ordered = !subtreeHasMedium(GRT_MAKE_REF(GRT_REF_NODE, b));
             uint32_t nk = 0;
-            for (uint32_t c : kids) {
-                if (type(c) == GRT_REF_NONE) continue;
-                Box bx;
-                uint32_t ref = c;
-                if (type(c) == GRT_REF_NODE) {
-                    // the ABI's node boxes are the fp64 geometry rounded outwards; the fp32 primitives the device tests
-                    // (v0, e0, e1 rounded separately) can sit an ulp OF THE LARGEST COORDINATE outside of them
-                    bx = nodeBox(idx(c));
-                    grow(bx, 5e-7);
-                    ref = GRT_MAKE_REF(GRT_REF_NODE, enqueue(idx(c)));
-                }
-                else { bx = refBox(c); ref = asRun(c); }
-                if (bx.empty()) continue;    // nothing below this child can be hit
-                for (int a = 0; a < 3; a++) { d[4 * a + nk] = down(bx.lo[a]); d[12 + 4 * a + nk] = up(bx.hi[a]); }
-                refs[nk++] = ref;
+            for (size_t k = 0; k < kref.size() && nk < 4; k++) {
+                if (type(kref[k]) == GRT_REF_NONE && !(kref[k] & GRT_DREF_RUN_BIT)) continue;
+                for (int a = 0; a < 3; a++) { d[4 * a + nk] = down(kbox[k].lo[a]); d[12 + 4 * a + nk] = up(kbox[k].hi[a]); }
+                refs[nk++] = kref[k];
             }
             meta[0] = ordered ? 1u : 0u;
             meta[1] = nk;
@@ -143,14 +234,13 @@ class Builder {
         }
         // stack needs
         needW.assign(R.n_wide, -1);
-        Rp = &R;
-        R.need_main = needRef(wideRef(root)) + 2;
+        R.need_main = needRef(R.root) + 2;
         R.need_boundary = 0;
-        for (const GrtMedium& m : M) R.need_boundary = std::max(R.need_boundary, needRef(wideRef(m.boundary)) + 2);
+        for (uint32_t b : R.media_boundary) R.need_boundary = std::max(R.need_boundary, needRef(b) + 2);
         return R.error.empty();
     }
 
-    // a ref as the device sees it: NODE refs index the wide array
+    // a remapped ABI ref held outside the node array (list entries of list-only scenes) as the device sees it
     uint32_t wideRef(uint32_t r) const {
         if (type(r) == GRT_REF_NODE) return GRT_MAKE_REF(GRT_REF_NODE, Rp->node_map[idx(r)]);
         return r;
@@ -161,8 +251,38 @@ class Builder {
     const std::vector<GrtNode>& N;
     const std::vector<uint32_t>& E;
     const std::vector<GrtMedium>& M;
-    std::vector<int> hasMedium, needW;
+    std::vector<int> hasMedium, needW, height;
     Result* Rp = nullptr;
+    bool wideLists = false;
+    // collapse order (A/B knob, results are identical): 0 = largest box first, 1 = tallest subtree first, 2 = largest box,
+    // tallest near the leaves
+    int mode = getenv("GRT_WIDE_MODE") ? atoi(getenv("GRT_WIDE_MODE")) : 2;
+    int bottomH = getenv("GRT_WIDE_BOTTOM") ? atoi(getenv("GRT_WIDE_BOTTOM")) : 2;
+
+    // the items of the list starting at entry e0, as device refs of runs (long runs split) or remapped ABI refs
+    void listItems(uint32_t e0, std::vector<uint32_t>& out) const {
+        for (uint32_t k = e0;; k++) {
+            const uint32_t e = E[2 * k], cnt = E[2 * k + 1], first = e & ~GRT_LIST_LAST;
+            if (isPrim(type(first))) {
+                for (uint32_t at = 0; at < cnt; at += GRT_DREF_RUN_MAX_COUNT) {
+                    const uint32_t c = std::min(cnt - at, GRT_DREF_RUN_MAX_COUNT);
+                    if (idx(first) + at + c - 1 > GRT_DREF_RUN_INDEX_MASK) { for (uint32_t j = 0; j < c; j++) out.push_back(first + at + j); continue; }
+                    out.push_back(GRT_DREF_RUN_BIT | (type(first) << GRT_REF_SHIFT) | ((c - 1) << GRT_DREF_RUN_INDEX_BITS) | (idx(first) + at));
+                }
+            } else if (type(first) != GRT_REF_NONE) out.push_back(first);
+            if (e & GRT_LIST_LAST) break;
+        }
+    }
+    Box itemBox(uint32_t it) const {
+        if (it & GRT_DREF_RUN_BIT) {
+            Box b = Box::none();
+            const uint32_t t = (it >> GRT_REF_SHIFT) & 7u, cnt = ((it >> GRT_DREF_RUN_INDEX_BITS) & 7u) + 1u, first = it & GRT_DREF_RUN_INDEX_MASK;
+            for (uint32_t j = 0; j < cnt; j++) b.add(primBox(t, first + j));
+            return b;
+        }
+        if (type(it) == GRT_REF_NODE) { Box b = nodeBox(idx(it)); grow(b, 5e-7); return b; }
+        return refBox(it);
+    }
 
     static uint32_t type(uint32_t r) { return GRT_REF_TYPE(r); }
     static uint32_t idx(uint32_t r) { return r & GRT_REF_MASK; }
@@ -197,6 +317,7 @@ class Builder {
     }
 
     bool subtreeHasMedium(uint32_t r) {
+        if (r & GRT_DREF_RUN_BIT) return false;
         switch (type(r)) {
             case GRT_REF_MEDIUM: return true;
             case GRT_REF_NODE: {

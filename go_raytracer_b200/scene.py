@@ -51,6 +51,11 @@ class Scene:
         img = N.host_check(self._L.grt_host_image(self._h, w, h, rgb.ctypes.data))
         return N.host_check(self._L.grt_host_image_texture(self._h, img))
 
+    def NewImageTexture(self, filename):
+        """hittable.NewImageTexture(filename) (texture.go:66-68 -> imageLoader.LoadImage): JPEG files are decoded with
+        Go's image/jpeg arithmetic (csrc/jpeg_go.hpp), so the texels are the reference's."""
+        return self.NewImageTextureFromArray(load_image(filename))
+
     def NewNoiseTextureWithType(self, scale, variant, seed=1):
         return N.host_check(self._L.grt_host_noise_texture(self._h, float(scale), int(variant), int(seed)))
 
@@ -185,6 +190,22 @@ class Scene:
     def description_ptr(self):
         """Opaque pointer for the test oracle (tests / bench cpu baseline only)."""
         return self._L.grt_host_scene_description(self._h)
+
+
+def decode_jpeg(data):
+    """imageLoader.LoadImage on JPEG bytes -> uint8 [H, W, 3], texel for texel what Go's image/jpeg + color.YCbCr give."""
+    L = N.lib()
+    buf = (C.c_ubyte * len(data)).from_buffer_copy(data)
+    w, h = C.c_int(0), C.c_int(0)
+    N.host_check(L.grt_host_decode_jpeg(buf, len(data), C.byref(w), C.byref(h), None, 0))
+    out = np.zeros((h.value, w.value, 3), dtype=np.uint8)
+    N.host_check(L.grt_host_decode_jpeg(buf, len(data), C.byref(w), C.byref(h), out.ctypes.data, out.nbytes))
+    return out
+
+
+def load_image(filename):
+    with open(filename, "rb") as f:
+        return decode_jpeg(f.read())
 
 
 def builtin_scene(scene_id, width=0, spp=0, aspect=0.0, seed=0, mesh_segments=0, image=None):

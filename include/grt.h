@@ -257,6 +257,9 @@ typedef struct GrtOptions {
     uint32_t pad;
 } GrtOptions;
 #define GRT_OPT_STATS 1u             /* fill GrtStats (slower: counts events) */
+#define GRT_OPT_TIMING 4u            /* time each kernel class of the render with CUDA events on the launching stream
+                                        (the wavefront variant then issues plain launches instead of its CUDA graph);
+                                        read the result with grt_last_timing() after synchronising */
 #define GRT_OPT_ATOMIC_SUM 2u        /* accumulate into rgb_sum with system-scope atomics: several renders, also from
                                         peer GPUs over NVLink, may then share one buffer (grt_render_multi does) */
 
@@ -326,6 +329,19 @@ int grt_render_device(GrtSceneHandle h, const GrtCamera* cam, const GrtOptions* 
  * (color.go:14-46).  DEVICE buffers. */
 int grt_tonemap_device(const float* d_rgb_sum, uint8_t* d_rgb8, uint64_t n_values,
                        float scale, void* stream);
+
+/* Device time per kernel class of the calling thread's last render that had GRT_OPT_TIMING set (CUDA events on the
+ * launching stream; measurement support for bench.py's roofline).  Megakernel renders report everything
+ * as `extend_ms` = `total_ms` (one kernel does the whole path). */
+typedef struct GrtTiming {
+    double   total_ms;               /* first launch .. last launch of the render                         */
+    double   generate_ms;            /* camera rays            camera.go:256-290                          */
+    double   extend_ms;              /* BVH traversal + primitive intersection (the dominant kernel)      */
+    double   shade_ms;               /* BSDF scatter, PDF mixture, clamp unwind, accumulation             */
+    uint64_t extend_launches;
+    uint64_t launches;
+} GrtTiming;
+int grt_last_timing(GrtTiming* out);
 
 /* In-process multi-GPU render: replicates the scene on devices[0..n), splits
  * the strata set s = g mod n, and combines the fp32 sums with one ncclReduce

@@ -46,6 +46,9 @@ void grt_host_scene_free(GrtHostScene* s);
 int grt_host_solid_color(GrtHostScene* s, double r, double g, double b);                 /* NewSolidColor            */
 int grt_host_checkerboard(GrtHostScene* s, double scale, int even_tex, int odd_tex);     /* NewCheckerboard          */
 int grt_host_image(GrtHostScene* s, int w, int h, const uint8_t* rgb);                   /* decoded RTImage          */
+/* LoadImage for a JPEG held in memory, with the arithmetic of Go's image/jpeg and color.YCbCr (imageLoader.go:28-84):
+ * call with rgb == NULL to get the size, then with a width*height*3 buffer.  Baseline JPEG only. */
+int grt_host_decode_jpeg(const uint8_t* data, size_t n, int* width, int* height, uint8_t* rgb, size_t cap);
 int grt_host_image_texture(GrtHostScene* s, int image);                                  /* NewImageTexture          */
 int grt_host_noise_texture(GrtHostScene* s, double scale, int variant, uint64_t seed);   /* NewNoiseTextureWithType  */
 /* materials — materials.go */

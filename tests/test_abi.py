@@ -108,9 +108,7 @@ int main(void) {
 """
 
 
-def test_plain_c99_client_compiles_links_and_runs(tmp_path):
-    """include/*.h are C headers (no C++ in the signatures) and the library is usable from plain C: builds a C99
-    client with gcc, links it against libgrt_cuda.so and runs it.  On a GPU box the client also renders."""
+def _run_c_client(tmp_path):
     import shutil
     import subprocess
     if not shutil.which("gcc"):
@@ -124,3 +122,19 @@ def test_plain_c99_client_compiles_links_and_runs(tmp_path):
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0, f"C client failed with code {r.returncode}: {r.stdout} {r.stderr}"
     assert "c client ok" in r.stdout
+    return r.stdout
+
+
+def test_plain_c99_client_compiles_links_and_runs(tmp_path):
+    """include/*.h are C headers (no C++ in the signatures) and the library is usable from plain C: builds a C99
+    client with gcc, links it against libgrt_cuda.so and runs it.  Without a device the client checks that upload fails
+    with GRT_E_NO_DEVICE and a message (no CPU fallback); test_plain_c99_client_renders_on_the_gpu is its GPU twin."""
+    _run_c_client(tmp_path)
+
+
+@pytest.mark.gpu
+def test_plain_c99_client_renders_on_the_gpu(tmp_path):
+    """The same C99 client under `-m gpu`: grt_scene_upload + grt_render with host buffers from plain C — the calls a
+    cgo binding makes."""
+    out = _run_c_client(tmp_path)
+    assert "0 devices" not in out

@@ -127,9 +127,11 @@ def test_render_follows_oracle_sample_by_sample(sid, w, spp):
     fin = np.isfinite(om) & np.isfinite(gm)
     assert fin.mean() > 0.999
     d = np.abs(gm - om)[fin]
-    # chaotic scenes (metal fuzz, media, dielectrics) diverge on a few samples; Lambertian-only scenes do not
+    # chaotic scenes (metal fuzz, dielectrics, the mesh's shared edges) diverge on a few samples; the others do not.
+    # Bars per scene, a little below what round 2 measured on B200 (tests/test_gpu_parity_configs.py lists the values)
     frac_same = (d < 1e-4).mean()
-    assert frac_same > (0.995 if sid in (6, 3, 4, 5) else 0.6), f"scene {sid}: only {frac_same:.3f} of pixel-channels follow the oracle"
+    bar = {6: 0.995, 3: 0.995, 4: 0.995, 5: 0.995, 7: 0.99, 1: 0.98, 2: 0.97, 8: 0.90}[sid]
+    assert frac_same > bar, f"scene {sid}: only {frac_same:.4f} of pixel-channels follow the oracle (bar {bar})"
     assert abs(gm[fin].mean() - om[fin].mean()) <= 1e-3 * max(1.0, om[fin].mean()), "mean RGB error above the 1e-3 budget"
 
 
@@ -417,6 +419,25 @@ def test_in_process_multi_gpu_matches_single_gpu():
             fin = np.isfinite(one) & np.isfinite(two)
             assert fin.mean() > 0.999
             assert np.allclose(two[fin], one[fin], rtol=1e-4, atol=1e-4), f"scene {sid} p2p={p2p}"
+    # the devices really render at the same time (one host thread per device): a BVH scene goes through the wavefront
+    # variant, whose bounce loop blocks its caller, so from one thread the two shards would run back to back
+    import time
+    s, cfg = g.builtin_scene(1, width=1200, spp=100)
+    cam = g.derive_camera(cfg)
+    flat = s.flatten()
+    opt = N.GrtOptions()
+    opt.seed, opt.variant = 0xC0FFEE, g.GRT_VARIANT_AUTO
+    out = np.zeros(cam.width * cam.height * 3, dtype=np.float32)
+    wall = {}
+    for n in (1, 2, 1, 2):
+        devs = (C.c_int * n)(*range(n))
+        ms = C.c_double(0)
+        out[:] = 0
+        t0 = time.perf_counter()
+        N.check(N.lib().grt_render_multi(C.byref(flat), C.byref(cam), C.byref(opt), devs, n, out.ctypes.data, None, C.byref(ms)))
+        wall[n] = (time.perf_counter() - t0, ms.value)           # the second round is warm
+    assert wall[2][1] < 0.7 * wall[1][1], f"two devices: {wall[2][1]:.1f} ms of device time vs {wall[1][1]:.1f} ms on one"
+    assert wall[2][0] < 0.85 * wall[1][0], f"two devices: {1e3 * wall[2][0]:.1f} ms wall vs {1e3 * wall[1][0]:.1f} ms on one (shards not concurrent?)"
 
 
 @pytest.mark.parametrize("seed", range(8))

@@ -14,16 +14,23 @@ import parity_util as PU
 import ref_render_util as RU
 
 
+def _earth():
+    """earthmap.jpg as Go decodes it (tests/golden/make_earthmap_fixture.py, csrc/jpeg_go.hpp)."""
+    import os
+    return np.load(os.path.join(RU.HERE, "golden", "earthmap_rgb8.npz"))["rgb"]
+
+
 def _quads_mask(cfg_like_width):
-    """Pixels of the `quads` scene (main.go:219-246) whose colour does not depend on Go's unseeded math/rand (Perlin
-    tables) or on Go's JPEG decoder (earth texels): the sky, the light quad (z = 0) and the teal quad (y = -3),
-    found by tracing one ray through every pixel centre region and eroded by two pixels."""
-    s, cfg = g.builtin_scene(5, width=cfg_like_width, spp=1)
+    """Pixels of the `quads` scene (main.go:219-246) whose colour does not depend on Go's unseeded math/rand (the Perlin
+    tables of the right quad, which the metal quad also reflects): the sky, the light quad (z = 0), the teal quad
+    (y = -3) and the earth-textured quad (x = -3; its texels are Go's, test_jpeg_go.py), found by tracing one ray
+    through every pixel and eroded by two pixels."""
+    s, cfg = g.builtin_scene(5, width=cfg_like_width, spp=1, image=_earth())
     cam = O.derived_camera(cfg)
     rays = PU.primary_batch(cfg, (0, 0, cam.width, cam.height))
     oh = O.OracleWorld(s).trace_batch(rays)
     p = oh["p"]
-    ok = (oh["id"] < 0) | (np.abs(p[:, 2]) < 1e-6) | (np.abs(p[:, 1] + 3.0) < 1e-6)
+    ok = (oh["id"] < 0) | (np.abs(p[:, 2]) < 1e-6) | (np.abs(p[:, 1] + 3.0) < 1e-6) | (np.abs(p[:, 0] + 3.0) < 1e-6)
     m = ok.reshape(cam.height, cam.width)
     er = m.copy()
     for dy in range(-2, 3):
@@ -49,12 +56,12 @@ def test_oracle_reproduces_the_go_renders(name):
 
 
 def test_oracle_reproduces_the_go_quads_render_on_its_deterministic_pixels():
-    s, cfg = g.builtin_scene(5)                             # main.go:237-240 as shipped: 400x400, 100 spp
+    s, cfg = g.builtin_scene(5, image=_earth())             # main.go:237-240 as shipped: 400x400, 100 spp
     cam = O.derived_camera(cfg)
     assert (cam.width, cam.height, cam.spp_sqrt) == (400, 400, 10)
     sums, _, _, _ = O.OracleWorld(s).render(cfg)
     mask = _quads_mask(400)
-    assert mask.mean() > 0.4
+    assert mask.mean() > 0.5
     RU.assert_matches_reference(RU.print_color(sums, 100), "quads", "oracle", mask)
 
 
@@ -78,7 +85,7 @@ def test_cuda_render_reproduces_the_go_renders(name, variant):
 @pytest.mark.gpu
 @pytest.mark.parametrize("variant", ["mega", "wavefront"])
 def test_cuda_render_reproduces_the_go_quads_render_on_its_deterministic_pixels(variant):
-    s, cfg = g.builtin_scene(5)
+    s, cfg = g.builtin_scene(5, image=_earth())
     cam = g.derive_camera(cfg)
     v = g.GRT_VARIANT_MEGAKERNEL if variant == "mega" else g.GRT_VARIANT_WAVEFRONT
     _, rgb8, _ = g.DeviceScene(s).render(cam, seed=0xBEEF, variant=v, want_rgb8=True)

@@ -1,12 +1,14 @@
 """Render one built-in scene once on the GPU (profiling helper): python tools/render_scene.py <scene> [width] [spp]"""
-import sys
+import sys, os
 sys.path.insert(0, ".")
 import numpy as np
 import go_raytracer_b200 as g
-import torch, os
+import torch
 VAR = int(os.environ.get("GRT_VARIANT", "0"))
 sid = int(sys.argv[1]); width = int(sys.argv[2]) if len(sys.argv) > 2 else 0; spp = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 cw = int(sys.argv[4]) if len(sys.argv) > 4 else None; cl = int(sys.argv[5]) if len(sys.argv) > 5 else None
+if os.environ.get("CL"):   # flatten options from the environment (A/B scripts): collapse_whole, collapse_leaf
+    cw, cl = int(os.environ.get("CW", "32")), int(os.environ["CL"])
 kw = {}
 if sid in (2, 5):
     kw["image"] = np.load("tests/golden/earthmap_rgb8.npz")["rgb"]
