@@ -455,8 +455,21 @@ struct TravState {
     static constexpr int STACK = BOUNDARY ? GRT_STACK_BOUNDARY : GRT_STACK_MAIN;
     static constexpr int NSMEM = STRIDE == 1 ? 0 : NS;   // entries held in shared memory; deeper ones overflow
     uint32_t local[STACK - NSMEM > 0 ? STACK - NSMEM : 1];
-    uint32_t* ext;
-    __device__ __forceinline__ uint32_t& at(int i) { return (STRIDE == 1 || i >= NSMEM) ? local[i - NSMEM] : ext[i * STRIDE]; }
+    uint32_t ext;        // shared-window address of this thread's column (set with set_ext)
+    // Explicit ld.shared / st.shared: a reference chosen at run time between the local array and the shared column made
+    // every push and pop a GENERIC load / store (the kernels held no LDS / STS at all, cuobjdump round 2), which costs an
+    // address-space lookup in the LSU and shows up as long-scoreboard stalls on the stack lines.
+    __device__ __forceinline__ void set_ext(const uint32_t* column) { ext = (uint32_t)__cvta_generic_to_shared(column); }
+    __device__ __forceinline__ uint32_t get(int i) const {
+        if (STRIDE == 1 || i >= NSMEM) return local[i - NSMEM];
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(ext + (uint32_t)i * (uint32_t)(STRIDE * 4)) : "memory");
+        return v;
+    }
+    __device__ __forceinline__ void put(int i, uint32_t v) {
+        if (STRIDE == 1 || i >= NSMEM) { local[i - NSMEM] = v; return; }
+        asm volatile("st.shared.u32 [%0], %1;" : : "r"(ext + (uint32_t)i * (uint32_t)(STRIDE * 4)), "r"(v) : "memory");
+    }
     int sp;
     float tmax;          // the closest t so far; plays the role of rayT.Max (bvh.go:78)
     uint32_t ref;        // the closest primitive so far, GRT_REF_NONE: none
@@ -464,7 +477,7 @@ struct TravState {
 };
 template <typename TS>
 __device__ __forceinline__ void trav_begin(TS& ts, uint32_t root, float tmax) {
-    ts.at(0) = root; ts.sp = 1; ts.tmax = tmax; ts.ref = GRT_MAKE_REF(GRT_REF_NONE, 0); ts.u = 0; ts.v = 0;
+    ts.put(0, root); ts.sp = 1; ts.tmax = tmax; ts.ref = GRT_MAKE_REF(GRT_REF_NONE, 0); ts.u = 0; ts.v = 0;
 }
 
 template <uint32_t FEAT, bool BOUNDARY, bool STATS>
@@ -585,12 +598,12 @@ __device__ __forceinline__ bool trav_run(const SceneView& sv, TS& ts, const RayD
                     idx++;
                     continue;
                 }
-                if (!last) ts.at(sp++) = GRT_MAKE_REF(GRT_REF_LIST, idx + 1);   // the rest of the list, after this item
+                if (!last) ts.put(sp++, GRT_MAKE_REF(GRT_REF_LIST, idx + 1));   // the rest of the list, after this item
                 break;
             }
             type = GRT_REF_TYPE(ref);
             idx = ref & GRT_REF_MASK;
-            if (type == GRT_REF_LIST || type == GRT_REF_NODE) { ts.at(sp++) = ref; return; }   // nested list / a BVH inside a list: next pop
+            if (type == GRT_REF_LIST || type == GRT_REF_NODE) { ts.put(sp++, ref); return; }   // nested list / a BVH inside a list: next pop
             if (type == GRT_REF_NONE) return;
         }
         if (!BOUNDARY && (FEAT & F_MEDIUM) && type == GRT_REF_MEDIUM) {
@@ -665,20 +678,20 @@ __device__ __forceinline__ bool trav_run(const SceneView& sv, TS& ts, const RayD
         GRT_CSWAP(0, 1) GRT_CSWAP(2, 3) GRT_CSWAP(0, 2) GRT_CSWAP(1, 3) GRT_CSWAP(1, 2)
 #undef GRT_CSWAP
         if (k0 < INF) {
-            if (k3 < INF) ts.at(sp++) = c3;
-            if (k2 < INF) ts.at(sp++) = c2;
-            if (k1 < INF) ts.at(sp++) = c1;
+            if (k3 < INF) ts.put(sp++, c3);
+            if (k2 < INF) ts.put(sp++, c2);
+            if (k1 < INF) ts.put(sp++, c1);
             ref = c0;
             return true;
         }
         if (sp == 0) { ref = GRT_MAKE_REF(GRT_REF_NONE, 0); return false; }
-        ref = ts.at(--sp);
+        ref = ts.get(--sp);
         return true;
     };
 
     if (!VOTE) {
         while (sp > 0) {
-            uint32_t ref = ts.at(--sp);
+            uint32_t ref = ts.get(--sp);
             if (FEAT & F_NODE) {
                 // walk down through inner nodes first ("while-while" traversal)
                 while (GRT_REF_TYPE(ref) == GRT_REF_NODE) if (!node_step(ref)) break;
@@ -696,7 +709,7 @@ __device__ __forceinline__ bool trav_run(const SceneView& sv, TS& ts, const RayD
         const uint32_t NONE = GRT_MAKE_REF(GRT_REF_NONE, 0);
         const int n_enter = __popc(__ballot_sync(mask, sp > 0));
         uint32_t ref = NONE;
-        if (sp > 0) ref = ts.at(--sp);
+        if (sp > 0) ref = ts.get(--sp);
         for (;;) {
             const bool have = GRT_REF_TYPE(ref) != GRT_REF_NONE;
             const bool on_node = (FEAT & F_NODE) && GRT_REF_TYPE(ref) == GRT_REF_NODE;
@@ -709,9 +722,9 @@ __device__ __forceinline__ bool trav_run(const SceneView& sv, TS& ts, const RayD
                 leaf(ref);
                 ref = NONE;
             }
-            if (GRT_REF_TYPE(ref) == GRT_REF_NONE && sp > 0) ref = ts.at(--sp);
+            if (GRT_REF_TYPE(ref) == GRT_REF_NONE && sp > 0) ref = ts.get(--sp);
         }
-        if (GRT_REF_TYPE(ref) != GRT_REF_NONE) ts.at(sp++) = ref;
+        if (GRT_REF_TYPE(ref) != GRT_REF_NONE) ts.put(sp++, ref);
     }
     ts.sp = sp; ts.tmax = tmax; ts.ref = hit.ref; ts.u = hit.u; ts.v = hit.v;
     return sp == 0;

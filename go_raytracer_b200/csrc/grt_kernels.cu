@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(GRT_MEGA_THREADS, mega_min_blocks(FEAT)) rende
     constexpr bool RESUMABLE = mega_resumable(FEAT);
     __shared__ uint32_t trav_smem[RESUMABLE ? GRT_TRAV_SMEM : 1][RESUMABLE ? GRT_MEGA_THREADS : 1];
     TravState<false, RESUMABLE ? GRT_MEGA_THREADS : 1> ts;
-    ts.ext = &trav_smem[0][RESUMABLE ? threadIdx.x : 0];
+    ts.set_ext(&trav_smem[0][RESUMABLE ? threadIdx.x : 0]);
     ts.sp = 0;
     bool tracing = false;
     uint32_t med_count = 0;

@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(256, WF_EXT_MIN_BLOCKS) wf_extend(const __grid
             HitInfo h;
             const float INF = __int_as_float(0x7f800000);
             TravState<false, BVH ? 256 : 1, WF_EXT_SMEM> ts;
-            ts.ext = &trav_smem[0][BVH ? threadIdx.x : 0];
+            ts.set_ext(&trav_smem[0][BVH ? threadIdx.x : 0]);
             trav_begin(ts, P.scene.root, INF);
             trav_run<TF, false, false, false>(sv, ts, ray, 0.001f, s3.w, __float_as_uint(s1.w), &mr, nullptr, 0u, 0);
             const bool hit = trav_end<FEAT>(sv, ts, ray, h);
@@ -160,6 +160,9 @@ __global__ void __launch_bounds__(256, WF_EXT_MIN_BLOCKS) wf_extend(const __grid
 // their hit, enqueue the slot and fetch the next live slot from a global counter.  Slots are independent, so
 // unlike the megakernel nothing ties a lane to a pixel.
 #define WF_DYN_THREADS 128
+#ifndef WF_DYN_SMEM
+#define WF_DYN_SMEM 24   /* traversal-stack entries per thread in shared memory (deeper ones in local memory): 16 / 24 / 32 measure the same */
+#endif
 #ifndef WF_DYN_MIN_BLOCKS
 #define WF_DYN_MIN_BLOCKS 7   /* 72 registers, 28 warps/SM: measured best of 6/7/8 with the 4-wide BVH (430 / 462 / 442 Mpaths/s on the 1M-triangle mesh) */
 #endif
@@ -168,9 +171,9 @@ __global__ void __launch_bounds__(WF_DYN_THREADS, WF_DYN_MIN_BLOCKS) wf_extend_d
     extern __shared__ __align__(16) unsigned char smem[];
     SceneView sv = wf_view<STAGED>(P, smem);
     constexpr uint32_t TF = FEAT | (STAGED == 0 ? F_GMEM : 0u);
-    __shared__ uint32_t trav_smem[GRT_TRAV_SMEM][WF_DYN_THREADS];
-    TravState<false, WF_DYN_THREADS> ts;
-    ts.ext = &trav_smem[0][threadIdx.x];
+    __shared__ uint32_t trav_smem[WF_DYN_SMEM][WF_DYN_THREADS];
+    TravState<false, WF_DYN_THREADS, WF_DYN_SMEM> ts;
+    ts.set_ext(&trav_smem[0][threadIdx.x]);
     ts.sp = 0;
     const unsigned FULL = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31u;
@@ -181,16 +184,34 @@ __global__ void __launch_bounds__(WF_DYN_THREADS, WF_DYN_MIN_BLOCKS) wf_extend_d
     uint4 s3 = make_uint4(0, 0, 0, GRT_NO_ID);
     RayD ray;
     ray_setup<FEAT>(ray, mk3(0, 0, 0), mk3(0, 0, 1), 0.0f);
+    // Every pass of the loop: (1) lanes whose ray finished in the last slice hand their slot to the queue of its
+    // material class, (2) idle lanes take the next slots of the pool, (3) all lanes run one traversal slice.  The up to
+    // four counters involved (three queues + the pool cursor) are bumped by lane 0 back to back, so the warp waits for
+    // ONE atomic round trip per pass instead of four dependent ones (8.5 % of this kernel's stall samples, ncu round 2).
+    int q = -1;                 // queue of the ray this lane just finished (-1: none)
+    uint32_t done_slot = 0;
     for (;;) {
-        const unsigned need = __ballot_sync(FULL, !have);
-        if (need && !exhausted) {
-            const int leader = __ffs(need) - 1;
-            uint32_t base = 0;
-            if ((int)lane == leader) base = atomicAdd(P.counters + C_NEXT, (uint32_t)__popc(need));
-            base = __shfl_sync(FULL, base, leader);
-            if (base >= P.P) exhausted = true;
+        const unsigned m0 = __ballot_sync(FULL, q == 0), m1 = __ballot_sync(FULL, q == 1), m2 = __ballot_sync(FULL, q == 2);
+        const unsigned need = exhausted ? 0u : __ballot_sync(FULL, !have);
+        uint32_t b0 = 0, b1 = 0, b2 = 0, bn = 0;
+        if (lane == 0) {
+            if (m0) b0 = atomicAdd(P.counters + 0, (uint32_t)__popc(m0));
+            if (m1) b1 = atomicAdd(P.counters + 1, (uint32_t)__popc(m1));
+            if (m2) b2 = atomicAdd(P.counters + 2, (uint32_t)__popc(m2));
+            if (need) bn = atomicAdd(P.counters + C_NEXT, (uint32_t)__popc(need));
+            if (m0 | m1 | m2) atomicAdd(P.counters + C_LIVE, (uint32_t)__popc(m0 | m1 | m2));
+        }
+        b0 = __shfl_sync(FULL, b0, 0); b1 = __shfl_sync(FULL, b1, 0); b2 = __shfl_sync(FULL, b2, 0); bn = __shfl_sync(FULL, bn, 0);
+        if (q >= 0) {
+            const unsigned m = q == 0 ? m0 : (q == 1 ? m1 : m2);
+            const uint32_t base = q == 0 ? b0 : (q == 1 ? b1 : b2);
+            P.queues[(size_t)q * P.P + base + __popc(m & lt_mask)] = done_slot;
+            q = -1;
+        }
+        if (need) {
+            if (bn >= P.P) exhausted = true;
             if (!have) {
-                const uint32_t sl = base + (uint32_t)__popc(need & lt_mask);
+                const uint32_t sl = bn + (uint32_t)__popc(need & lt_mask);
                 if (sl < P.P) {
                     const uint4 v = P.S3[sl];
                     if (v.z != WF_FREE) {
@@ -210,7 +231,6 @@ __global__ void __launch_bounds__(WF_DYN_THREADS, WF_DYN_MIN_BLOCKS) wf_extend_d
         mr.pixel = s3.x; mr.sample = s3.y; mr.bounce = s3.z & 255u; mr.k0 = P.k0; mr.k1 = P.k1; mr.count = med_count;
         const bool fin = trav_run<TF, false, false, true>(sv, ts, ray, 0.001f, s3.w, self_ref, &mr, nullptr, FULL, P.exit16);
         med_count = mr.count;
-        int q = -1;
         if (have && fin) {
             HitInfo h;
             const bool hit = trav_end<FEAT>(sv, ts, ray, h);
@@ -225,21 +245,11 @@ __global__ void __launch_bounds__(WF_DYN_THREADS, WF_DYN_MIN_BLOCKS) wf_extend_d
                 q = (mt == GRT_MAT_DIFFUSE_LIGHT) ? Q_TERMINAL : ((mt == GRT_MAT_METAL || mt == GRT_MAT_DIELECTRIC) ? Q_SPECULAR : Q_DIFFUSE);
             }
             P.H[slot] = make_float4(h.t, __uint_as_float(h.ref), h.u, h.v);
+            done_slot = slot;
             have = false;
         }
-#pragma unroll
-        for (int k = 0; k < Q_COUNT; k++) {
-            unsigned m = __ballot_sync(FULL, q == k);
-            if (!m) continue;
-            uint32_t base = 0;
-            int leader = __ffs(m) - 1;
-            if ((int)lane == leader) base = atomicAdd(P.counters + k, (uint32_t)__popc(m));
-            base = __shfl_sync(FULL, base, leader);
-            if (q == k) P.queues[(size_t)k * P.P + base + __popc(m & lt_mask)] = slot;
-        }
-        unsigned live = __ballot_sync(FULL, q >= 0);
-        if (live && lane == 0) atomicAdd(P.counters + C_LIVE, (uint32_t)__popc(live));
     }
+    // (the loop only ends on a pass that found no lane with work, and such a pass has already flushed every pending q)
 }
 
 // ---- shade ------------------------------------------------------------------------------------------
@@ -336,11 +346,11 @@ template <uint32_t FEAT>
 static int wf_run(GrtSceneHandle h, WfParams& P, cudaStream_t st, uint32_t* h_counters, bool timing) {
     int rc = GRT_OK;
     // Persistent extend with dynamic ray fetch (wf_extend_dyn) vs one thread per slot (wf_extend), measured with the 4-wide
-    // BVH (profiles/README.md, round 2): triangle meshes 462 vs 232 Mpaths/s, the sphere BVH of book 1 796 vs 696; the
-    // book-2 cover (spheres + boxes + two media under one top-level list) 399 vs 458 — its rays alternate between node
-    // walks, fp64 sphere tests, box slabs and medium draws, and lock-step voting only adds waiting there.
+    // BVH, one primitive per leaf and lists as wide nodes (profiles/README.md, round 2): triangle meshes 462 vs 232
+    // Mpaths/s, the sphere BVH of book 1 796 vs 696, the book-2 cover 538 vs 510 — every BVH scene takes the persistent
+    // kernel now (round 1's binary tree with 4-primitive leaves had book 2 the other way round: 252 vs 311).
     constexpr bool can_dyn = (FEAT & F_NODE) != 0;
-    bool dyn = can_dyn && (((FEAT & F_TRI) != 0 && P.scene.n_tris >= 1024u) || FEAT == (V_SPHERES));
+    bool dyn = can_dyn;
     if (const char* e = getenv("GRT_WF_DYN")) dyn = can_dyn && (atoi(e) == 2 || (dyn && atoi(e) != 0));   // 0: never, 2: whenever compiled in
     const bool staged = grt_internal_staged(h) == 2 && !dyn;   // whole-blob staging or none
     const unsigned dyn_blocks = (unsigned)grt_internal_sm_count(h) * WF_DYN_MIN_BLOCKS;
