@@ -385,9 +385,15 @@ __device__ __forceinline__ ShadeResult shade_vertex(const SceneView& sv, const R
             if (!((FEAT & F_QUAD_LIGHT) && L->type == GRT_LIGHT_QUAD && quad_light_pdf_fast(sv.dlights() + i, s.p, dir, &pv))) {
                 // within fp32 error of a decision boundary (or not a quad): the reference's fp64 arithmetic.
                 // A direction sampled ON this light is regenerated in fp64 so that it cannot fall off its edge.
+#ifndef GRT_NO_FALLBACK_FENCE
+                asm volatile("" ::: "memory");   // keep the loads of this 0.1 % path from being scheduled above the branch
+#endif
                 d3 p64 = tod3(s.p);
                 d3 dir64 = (from_light && i == li) ? light_random<FEAT>(L, p64, r1, r2) : tod3(dir);
                 pv = (float)light_pdf<FEAT>(L, p64, dir64);
+#ifdef GRT_DEBUG_COUNT_F64
+                if (n_lightpdf) *n_lightpdf += 1000000u;   // (debug builds: counts fp64 fallbacks in the high digits of light_pdf_evals)
+#endif
             }
             lp += weight * pv;
         }
@@ -446,6 +452,35 @@ __device__ __forceinline__ f3 unwind_clamp(f3 T, uint32_t zinfo, f3 E, StackPtr 
         const int zx = (int)(zinfo & 255u), zy = (int)((zinfo >> 8) & 255u), zz = (int)((zinfo >> 16) & 255u);
         for (int i = 0; i < sp; i++) {
             const float4 rj = rstack[(size_t)i * stride];
+            float sj = (i >= zx ? L.x * rj.x : 0.0f) + (i >= zy ? L.y * rj.y : 0.0f) + (i >= zz ? L.z * rj.z : 0.0f);
+            worst = fmaxf(worst, sj);
+        }
+        if (zinfo & (1u << 24)) L.x = 0.0f;
+        if (zinfo & (1u << 25)) L.y = 0.0f;
+        if (zinfo & (1u << 26)) L.z = 0.0f;
+    }
+    if (worst > max_contribution) L = L * fast_div(max_contribution, worst);
+    return L;
+}
+
+// The same unwind for a stack whose first NS entries live in shared memory (`near(i)`) and the rest in local memory
+// (`deep(i)`), as the megakernel keeps it.  One predicated, fully unrolled pass over the NS near entries and a (rare)
+// loop over the deep ones: choosing the memory per element inside one loop compiled to a branch per entry (7 % of
+// the Cornell kernel's instructions, ncu round 2).
+template <int NS, class Near, class Deep>
+__device__ __forceinline__ f3 unwind_clamp_split(f3 T, uint32_t zinfo, f3 E, Near near, Deep deep, int sp, float max_contribution) {
+    f3 L = T * E;
+    float worst = 0.0f;
+    if (zinfo == 0u) {
+#pragma unroll
+        for (int i = 0; i < NS; i++) {
+            if (i < sp) { const float4 rj = near(i); worst = fmaxf(worst, fmaf(L.x, rj.x, fmaf(L.y, rj.y, L.z * rj.z))); }
+        }
+        for (int i = NS; i < sp; i++) { const float4 rj = deep(i); worst = fmaxf(worst, fmaf(L.x, rj.x, fmaf(L.y, rj.y, L.z * rj.z))); }
+    } else {
+        const int zx = (int)(zinfo & 255u), zy = (int)((zinfo >> 8) & 255u), zz = (int)((zinfo >> 16) & 255u);
+        for (int i = 0; i < sp; i++) {
+            const float4 rj = i < NS ? near(i) : deep(i);
             float sj = (i >= zx ? L.x * rj.x : 0.0f) + (i >= zy ? L.y * rj.y : 0.0f) + (i >= zz ? L.z * rj.z : 0.0f);
             worst = fmaxf(worst, sj);
         }

@@ -29,7 +29,10 @@ enum : uint32_t {
     F_TMIN_F64 = 1u << 16,
     // not a scene feature either: the scene arrays are read from global memory (nothing staged in shared memory), so the
     // traversal fetches them through the read-only path (ld.global.nc, __ldg) instead of generic loads
-    F_GMEM = 1u << 18
+    F_GMEM = 1u << 18,
+    // the first SceneView::tl_n nodes (the top of the tree: nodes are numbered breadth first) are also held in shared
+    // memory by this kernel and fetched from there
+    F_TREELET = 1u << 19
 };
 // Which loads take the read-only path: the node fetches always do (F_GMEM); the primitive records only where it paid —
 // ptxas schedules ld.global.nc loads earlier and wider, which cost the all-feature extend kernel 1.1 KB of spills.
@@ -102,6 +105,7 @@ struct SceneView {
     const unsigned char* base;
     const unsigned char* cold;
     const DevScene* ds;
+    uint32_t tl = 0, tl_n = 0;   // F_TREELET: shared-window address of the staged top-of-tree nodes, and how many
     __device__ __forceinline__ const float4* nodes() const { return (const float4*)(base + ds->off_nodes); }
     __device__ __forceinline__ const GrtSphere* spheres() const { return (const GrtSphere*)(base + ds->off_spheres); }
     __device__ __forceinline__ const DQuadHot* quads() const { return (const DQuadHot*)(base + ds->off_quads); }
@@ -653,10 +657,25 @@ __device__ __forceinline__ bool trav_run(const SceneView& sv, TS& ts, const RayD
     auto node_step = [&](uint32_t& ref) -> bool {   // false: the stack ran dry
         const float4* np = nodes + GRT_WNODE_F4 * (ref & GRT_REF_MASK);
         constexpr bool NC = GRT_NC_NODES != 0 && (FEAT & F_GMEM) != 0;   // 128-bit read-only (ld.global.nc) fetches unless the nodes sit in shared memory
-        const float4 pnx = ldro<NC>(np + r.nx), pny = ldro<NC>(np + r.ny), pnz = ldro<NC>(np + r.nz);
-        const float4 pfx = ldro<NC>(np + (3u - r.nx)), pfy = ldro<NC>(np + (5u - r.ny)), pfz = ldro<NC>(np + (7u - r.nz));
-        const uint4 ch = ldro<NC>((const uint4*)(np + 6));
-        const uint2 meta = ldro<NC>((const uint2*)(np + 7));
+        float4 pnx, pny, pnz, pfx, pfy, pfz;
+        uint4 ch;
+        uint2 meta;
+        const uint32_t ni = ref & GRT_REF_MASK;
+        if ((FEAT & F_TREELET) && ni < sv.tl_n) {
+            // the top of the tree, staged in shared memory by this block (128-bit ld.shared)
+            const uint32_t a = sv.tl + ni * (GRT_WNODE_F4 * 16u);
+            auto lds4 = [](uint32_t addr) { float4 v; asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr)); return v; };
+            pnx = lds4(a + 16u * r.nx); pny = lds4(a + 16u * r.ny); pnz = lds4(a + 16u * r.nz);
+            pfx = lds4(a + 16u * (3u - r.nx)); pfy = lds4(a + 16u * (5u - r.ny)); pfz = lds4(a + 16u * (7u - r.nz));
+            const float4 c4 = lds4(a + 96u), m4 = lds4(a + 112u);
+            ch = make_uint4(__float_as_uint(c4.x), __float_as_uint(c4.y), __float_as_uint(c4.z), __float_as_uint(c4.w));
+            meta = make_uint2(__float_as_uint(m4.x), __float_as_uint(m4.y));
+        } else {
+            pnx = ldro<NC>(np + r.nx); pny = ldro<NC>(np + r.ny); pnz = ldro<NC>(np + r.nz);
+            pfx = ldro<NC>(np + (3u - r.nx)); pfy = ldro<NC>(np + (5u - r.ny)); pfz = ldro<NC>(np + (7u - r.nz));
+            ch = ldro<NC>((const uint4*)(np + 6));
+            meta = ldro<NC>((const uint2*)(np + 7));
+        }
         if (STATS) tc->box += meta.y;
         const float INF = __int_as_float(0x7f800000);
         const bool ordered = (meta.x & 1u) != 0u;

@@ -52,6 +52,7 @@ struct WfParams {
     float* rgb_sum;
     int sys_atomics;                  // rgb_sum may live on a peer GPU (grt_render_multi): system-scope atomics
     int exit16;                       // wf_extend_dyn: a traversal slice ends when fewer than exit16/16 lanes have work
+    uint32_t treelet_nodes;           // wf_extend_dyn<.., TREELET>: wide nodes staged in shared memory per block
 };
 
 template <int STAGED>
@@ -160,18 +161,38 @@ __global__ void __launch_bounds__(256, WF_EXT_MIN_BLOCKS) wf_extend(const __grid
 // their hit, enqueue the slot and fetch the next live slot from a global counter.  Slots are independent, so
 // unlike the megakernel nothing ties a lane to a pixel.
 #define WF_DYN_THREADS 128
+#ifndef WF_DYN_TREELET
+#define WF_DYN_TREELET 32         /* wide nodes (128 B each) staged in shared memory per block for trees of at least ... */
+#endif
+#ifndef WF_DYN_TREELET_MIN_NODES
+#define WF_DYN_TREELET_MIN_NODES 16384u   /* ... this many wide nodes (smaller trees are L1-resident: staging only shrinks the L1) */
+#endif
 #ifndef WF_DYN_SMEM
 #define WF_DYN_SMEM 24   /* traversal-stack entries per thread in shared memory (deeper ones in local memory): 16 / 24 / 32 measure the same */
 #endif
 #ifndef WF_DYN_MIN_BLOCKS
 #define WF_DYN_MIN_BLOCKS 7   /* 72 registers, 28 warps/SM: measured best of 6/7/8 with the 4-wide BVH (430 / 462 / 442 Mpaths/s on the 1M-triangle mesh) */
 #endif
-template <uint32_t FEAT, int STAGED>
+template <uint32_t FEAT, int STAGED, bool TREELET>
 __global__ void __launch_bounds__(WF_DYN_THREADS, WF_DYN_MIN_BLOCKS) wf_extend_dyn(const __grid_constant__ WfParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
     SceneView sv = wf_view<STAGED>(P, smem);
-    constexpr uint32_t TF = FEAT | (STAGED == 0 ? F_GMEM : 0u);
+    constexpr uint32_t TF = FEAT | (STAGED == 0 ? F_GMEM : 0u) | (TREELET ? F_TREELET : 0u);
     __shared__ uint32_t trav_smem[WF_DYN_SMEM][WF_DYN_THREADS];
+    // Top-of-tree nodes in shared memory (TREELET builds, large trees only): the wide nodes are numbered breadth first, so
+    // the first P.treelet_nodes of them are the levels every ray walks through; the block copies them once into its
+    // dynamic shared memory and node_step fetches them with ld.shared.  Measured (profiles/README.md, round 2): +1-2 % on
+    // the 1M-triangle mesh with 32 nodes, -3 ... -10 % on the small book scenes at any size (their whole tree already
+    // lives in the L1, and every KB of shared memory is a KB less of it), so small trees run the build without it.
+    if (TREELET) {
+        float4* treelet = (float4*)smem;
+        const uint32_t n = P.treelet_nodes * GRT_WNODE_F4;
+        const float4* src = sv.nodes();
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) treelet[i] = __ldg(src + i);
+        __syncthreads();
+        sv.tl = (uint32_t)__cvta_generic_to_shared(treelet);
+        sv.tl_n = P.treelet_nodes;
+    }
     TravState<false, WF_DYN_THREADS, WF_DYN_SMEM> ts;
     ts.set_ext(&trav_smem[0][threadIdx.x]);
     ts.sp = 0;
@@ -353,6 +374,13 @@ static int wf_run(GrtSceneHandle h, WfParams& P, cudaStream_t st, uint32_t* h_co
     bool dyn = can_dyn;
     if (const char* e = getenv("GRT_WF_DYN")) dyn = can_dyn && (atoi(e) == 2 || (dyn && atoi(e) != 0));   // 0: never, 2: whenever compiled in
     const bool staged = grt_internal_staged(h) == 2 && !dyn;   // whole-blob staging or none
+    {
+        uint32_t tl = WF_DYN_TREELET;
+        if (const char* e = getenv("GRT_WF_TREELET")) tl = (uint32_t)atoi(e);   // (A/B knob: nodes per block, 0 = off)
+        else if (P.scene.n_nodes < WF_DYN_TREELET_MIN_NODES) tl = 0;
+        P.treelet_nodes = dyn ? (tl < P.scene.n_nodes ? tl : P.scene.n_nodes) : 0u;
+        if (P.treelet_nodes > 256u) P.treelet_nodes = 256u;
+    }
     const unsigned dyn_blocks = (unsigned)grt_internal_sm_count(h) * WF_DYN_MIN_BLOCKS;
     const size_t smem = staged ? P.scene.stage_bytes : 0;
     const unsigned blocks = (P.P + 255) / 256;
@@ -380,7 +408,8 @@ static int wf_run(GrtSceneHandle h, WfParams& P, cudaStream_t st, uint32_t* h_co
         if (dyn) {
             if constexpr (can_dyn) {
                 // the scene is read from global memory (L1/L2): the shared memory holds the traversal stacks
-                wf_extend_dyn<FEAT, 0><<<dyn_blocks, WF_DYN_THREADS, 0, s_>>>(P);
+                if (P.treelet_nodes) wf_extend_dyn<FEAT, 0, true><<<dyn_blocks, WF_DYN_THREADS, P.treelet_nodes * GRT_WNODE_F4 * 16, s_>>>(P);
+                else wf_extend_dyn<FEAT, 0, false><<<dyn_blocks, WF_DYN_THREADS, 0, s_>>>(P);
                 mark(s_);
                 wf_shade<FEAT, 0, Q_TERMINAL><<<blocks, 256, 0, s_>>>(P);
                 wf_shade<FEAT, 0, Q_DIFFUSE><<<blocks, 256, 0, s_>>>(P);
