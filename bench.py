@@ -235,8 +235,7 @@ def measure_config(name, spp, steps, warmup, local, seed, cores, want_cpu, peaks
     torch.cuda.synchronize()
     T = last_timing(L)
     share = T.extend_ms / T.total_ms if T.total_ms > 0 else None
-    dominant = ("render_mega_kernel" if variant == "megakernel" else
-                ("wf_extend_dyn" if (flat.n_tris >= 1024 or (flat.n_spheres and not flat.n_quads and not flat.n_tris)) else "wf_extend"))
+    dominant = "render_mega_kernel" if variant == "megakernel" else "wf_extend_dyn"    # every BVH scene takes the persistent extend
     scene.close()
     cpu, ev, ev_src = None, None, None
     if want_cpu:
@@ -454,11 +453,15 @@ def run_ours(args):
     inproc = None
     if world > 1 and not args.no_inproc:
         sync()
+        # the other ranks wait on a CPU (gloo) barrier: an NCCL barrier is a kernel spinning on their GPUs, and rank 0 is
+        # about to use those GPUs from its own process
+        cpu_group = dist.new_group(backend="gloo")
         if rank == 0:
             try:
                 devs = (C.c_int * world)(*range(world))
                 opt = N.GrtOptions()
                 opt.seed, opt.variant = args.seed, variant
+                flat = s.flatten()          # (the view handed out earlier died with the e2e steps' own flatten calls)
                 hs = np.zeros(nval, dtype=np.float32)
                 kms = C.c_double(0)
                 os.environ["GRT_MULTI_P2P"] = "1"
@@ -472,6 +475,7 @@ def run_ours(args):
                           "mean": float(hs.mean() / S2)}
             except Exception as e:      # measurement extra: never fail the bench line over it
                 inproc = {"error": str(e)}
+        dist.barrier(group=cpu_group)
         sync()
 
     if rank == 0:
@@ -522,7 +526,7 @@ def run_ours(args):
             except Exception:
                 pass
             bind = rp["fp32"] if rp["bound"] == "fp32_issue" else rp["bytes"]
-            roofline = {"kernel": "render_mega_kernel" if vname == "mega" else "wf_extend / wf_extend_dyn (the wavefront variant's traversal + intersection kernel)",
+            roofline = {"kernel": "render_mega_kernel" if vname == "mega" else "wf_extend_dyn (the wavefront variant's traversal + intersection kernel)",
                         "bound": rp["bound"], "achieved": bind["achieved"], "peak": bind["peak"], "unit": bind["unit"], "frac": bind["frac"],
                         "peak_source": bind["peak_source"], "kernel_ms_per_step": T.extend_ms, "kernel_share_of_step": dom_share,
                         "kernel_launches_per_step": int(T.extend_launches),

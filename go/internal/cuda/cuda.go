@@ -18,6 +18,7 @@ import (
 	"errors"
 	"fmt"
 	"io"
+	"runtime"
 	"unsafe"
 
 	"github.com/nsp5488/go_raytracer/internal/hittable"
@@ -32,19 +33,35 @@ type CameraParams struct {
 	DefocusAngle, MaxContribution                   float64
 }
 
-// Options selects devices and the kernel variant (flags -gpus, -variant).
+// Variant names the render kernels (flag -variant): Auto lets the library pick per scene (the megakernel for list-only
+// scenes such as the Cornell boxes, the wavefront kernels for scenes with a BVH), like the C++ and Python mirrors do.
+type Variant int
+
+const (
+	Auto       Variant = C.GRT_VARIANT_AUTO
+	Megakernel Variant = C.GRT_VARIANT_MEGAKERNEL
+	Wavefront  Variant = C.GRT_VARIANT_WAVEFRONT
+)
+
+// Options selects devices and the kernel variant (flags -gpus, -variant).  The zero value renders on one GPU with
+// the variant chosen by the library.
 type Options struct {
-	Seed     uint64
-	Gpus     int
-	Wavefront bool
+	Seed    uint64
+	Gpus    int
+	Variant *Variant // nil: Auto
 }
 
+// lastError must run on the OS thread that made the failing call: the library keeps its error text per thread.
+// Every exported function of this package therefore pins its goroutine with runtime.LockOSThread for the duration
+// of its C calls (a goroutine that migrated between the call and grt_last_error would read an empty message).
 func lastError(rc C.int) error {
 	return fmt.Errorf("libgrt_cuda error %d: %s", int(rc), C.GoString(C.grt_last_error()))
 }
 
 // bvhOrder binds grt_bvh_order: BuildBVH's recursive sorts on the device (bvh.go:35-61).
 func bvhOrder(boxes []float64) ([]uint32, error) {
+	runtime.LockOSThread()
+	defer runtime.UnlockOSThread()
 	n := len(boxes) / 6
 	order := make([]uint32, n)
 	if n == 0 {
@@ -70,6 +87,8 @@ func DeviceCount() int { return int(C.grt_device_count()) }
 // to out.  tick is called H+1 times in total so that the progress bar finishes
 // (progress.go:47-54, camera.go:107,131).
 func Render(fs *hittable.FlatScene, cp CameraParams, opt Options, out io.Writer, tick func()) error {
+	runtime.LockOSThread() // grt_last_error is per OS thread; the CUDA context of grt_render is too
+	defer runtime.UnlockOSThread()
 	if DeviceCount() == 0 {
 		return errors.New("no CUDA device")
 	}
@@ -91,8 +110,9 @@ func Render(fs *hittable.FlatScene, cp CameraParams, opt Options, out io.Writer,
 	var o C.GrtOptions
 	o.seed = C.uint64_t(opt.Seed)
 	o.sample_stride = 1
-	if opt.Wavefront {
-		o.variant = C.GRT_VARIANT_WAVEFRONT
+	o.variant = C.GRT_VARIANT_AUTO
+	if opt.Variant != nil {
+		o.variant = C.int32_t(*opt.Variant)
 	}
 
 	n := cp.Width * cp.Height * 3

@@ -837,6 +837,27 @@ static int launch_mega(GrtSceneDev* h, RenderParams& P, bool stats, cudaStream_t
 
 int grt_render_wavefront(GrtSceneHandle h, const GrtCamera* cam, const GrtOptions* opt, float* d_rgb_sum, cudaStream_t st, GrtStats* d_stats);
 
+int grt_internal_resolve_variant(GrtSceneHandle h, const GrtOptions* opt, bool has_stats_buffer) {
+    if (opt->variant != GRT_VARIANT_AUTO) return opt->variant;
+    return ((h->ds.features & F_NODE) && !((opt->flags & GRT_OPT_STATS) && has_stats_buffer)) ? GRT_VARIANT_WAVEFRONT : GRT_VARIANT_MEGAKERNEL;
+}
+
+// dst[i] += src[i] with system-scope atomics: a device adds its private sums into the shared buffer of another device
+// over NVLink peer memory (grt_render_multi, wavefront shards)
+__global__ void peer_accumulate_kernel(float* __restrict__ dst, const float* __restrict__ src, uint64_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float v = src[i];
+    if (v != 0.0f) atomicAdd_system(dst + i, v);    // (NaN != 0 is true: a NaN sum is carried over, color.go:28-36)
+}
+int grt_internal_peer_accumulate(float* d_dst, const float* d_src, uint64_t n, cudaStream_t st) {
+    if (!n) return GRT_OK;
+    peer_accumulate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_dst, d_src, n);
+    grt_count_launch(1);
+    CUDA_TRY(cudaGetLastError());
+    return GRT_OK;
+}
+
 extern "C" int grt_render_device(GrtSceneHandle h, const GrtCamera* cam, const GrtOptions* opt, float* d_rgb_sum, void* stream, GrtStats* d_stats) {
     if (!h || !cam || !opt || !d_rgb_sum) { grt_set_error("grt_render_device: NULL argument"); return GRT_E_INVALID; }
     CUDA_TRY(cudaSetDevice(h->device));
@@ -844,9 +865,7 @@ extern "C" int grt_render_device(GrtSceneHandle h, const GrtCamera* cam, const G
     // AUTO: BVH scenes (book covers, meshes) go to the wavefront kernels, whose extend step copes with long, uneven
     // traversals and many material classes; tiny list scenes (Cornell) to the megakernel.  Event counters exist only
     // in the megakernel.
-    int variant = opt->variant;
-    if (variant == GRT_VARIANT_AUTO)
-        variant = ((h->ds.features & F_NODE) && !((opt->flags & GRT_OPT_STATS) && d_stats)) ? GRT_VARIANT_WAVEFRONT : GRT_VARIANT_MEGAKERNEL;
+    const int variant = grt_internal_resolve_variant(h, opt, d_stats != nullptr);
     if (variant == GRT_VARIANT_WAVEFRONT) return grt_render_wavefront(h, cam, opt, d_rgb_sum, st, d_stats);
     if (variant != GRT_VARIANT_MEGAKERNEL) { grt_set_error("unknown GrtOptions.variant"); return GRT_E_INVALID; }
     RenderParams P;

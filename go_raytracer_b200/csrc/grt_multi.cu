@@ -5,7 +5,10 @@
 // Fused path (NVLink / NVSwitch with native peer atomics): ONE accumulation buffer lives on devices[0], every other
 // device maps it as peer memory, and the render kernels add their per-pixel sums straight into it with system-scope
 // atomics as each pixel is retired — the exchange is spread over the whole render (12.6 MB of 4-byte reductions over
-// tens of milliseconds) instead of following it, and no collective runs at all.
+// tens of milliseconds) instead of following it, and no collective runs at all.  That holds for the megakernel, which
+// retires one sum per PIXEL.  The wavefront kernels retire one sum per PATH (paths of a pixel are spread over the pool),
+// and a remote atomic per path is 10^8 NVLink transactions per frame: there a peer device accumulates into a private
+// buffer at home and adds that buffer into the shared one once, at the end, with one system-scope atomic per value.
 // Fallback (no peer access): private buffers and ONE ncclReduce(sum, root = devices[0]) before tonemap.
 // The devices render concurrently (one host thread each); kernel_ms is the slowest device's e0..e1 time.
 // (bench.py instead runs one process per GPU and reduces through torch.distributed's NCCL communicator.)
@@ -19,6 +22,7 @@
 #include <string>
 #include <vector>
 #include <thread>
+#include <mutex>
 #include "grt_internal.h"
 
 namespace {
@@ -86,7 +90,6 @@ extern "C" int grt_render_multi(const GrtScene* scene, const GrtCamera* cam, con
     std::vector<cudaEvent_t> e0(n, nullptr), e1(n, nullptr);
     std::vector<ncclComm_t> comms(n, nullptr);
     uint8_t* d_rgb8 = nullptr;
-    bool comms_ok = false;
     float* d_shared = nullptr;      // fused path: the one accumulation buffer, plain cudaMalloc (peer-mappable) on devices[0]
     cudaEvent_t e_init = nullptr;
     float* d_total = nullptr;       // where the complete sums end up (on devices[0])
@@ -99,6 +102,10 @@ extern "C" int grt_render_multi(const GrtScene* scene, const GrtCamera* cam, con
         CU(cudaEventCreate(&e0[g]));
         CU(cudaEventCreate(&e1[g]));
         if (fused) {
+            if (g > 0 && grt_internal_resolve_variant(hs[g], opt, false) == GRT_VARIANT_WAVEFRONT) {
+                CU(grt_dev_alloc((void**)&d_sum[g], nval * sizeof(float)));     // private sums, added to the shared buffer at the end
+                CU(cudaMemsetAsync(d_sum[g], 0, nval * sizeof(float), st[g]));
+            }
             if (g == 0) {
                 CU(cudaMalloc((void**)&d_shared, nval * sizeof(float)));
                 CU(cudaMemcpyAsync(d_shared, rgb_sum, nval * sizeof(float), cudaMemcpyHostToDevice, st[0]));
@@ -116,7 +123,22 @@ extern "C" int grt_render_multi(const GrtScene* scene, const GrtCamera* cam, con
         if (g == 0) CU(cudaMemcpyAsync(d_sum[g], rgb_sum, nval * sizeof(float), cudaMemcpyHostToDevice, st[g]));
         else CU(cudaMemsetAsync(d_sum[g], 0, nval * sizeof(float), st[g]));
     }
-    if (n > 1 && !fused) { NC(g_nccl.CommInitAll(comms.data(), n, devices)); comms_ok = true; }
+    if (n > 1 && !fused) {
+        // communicators are kept for the life of the process (one set per device list): creating them costs ~0.3 s and the
+        // first collective on a fresh communicator another ~0.4 s of connection setup
+        static std::mutex cm;
+        static std::vector<int> kept_devs;
+        static std::vector<ncclComm_t> kept;
+        std::lock_guard<std::mutex> lk(cm);
+        if (kept_devs != std::vector<int>(devices, devices + n)) {
+            for (ncclComm_t c : kept) if (c) g_nccl.CommDestroy(c);
+            kept.assign(n, nullptr);
+            kept_devs.clear();
+            NC(g_nccl.CommInitAll(kept.data(), n, devices));
+            kept_devs.assign(devices, devices + n);
+        }
+        comms = kept;
+    }
 
     // every device renders its strata shard, concurrently: one host thread per device, because the wavefront variant's
     // bounce loop blocks its caller (it reads the live-path counter back between graph launches) — issued from one
@@ -130,11 +152,13 @@ extern "C" int grt_render_multi(const GrtScene* scene, const GrtCamera* cam, con
             o.sample_first = opt->sample_first + (uint32_t)g * base_stride;
             o.sample_stride = base_stride * (uint32_t)n;
             o.device = devices[g];
-            if (fused) o.flags |= GRT_OPT_ATOMIC_SUM;
+            const bool direct = fused && !d_sum[g];   // this shard adds straight into the shared buffer as it goes
+            if (direct) o.flags |= GRT_OPT_ATOMIC_SUM;
             cudaError_t e = cudaSetDevice(devices[g]);
             if (e == cudaSuccess) e = cudaEventRecord(e0[g], st[g]);
             if (e != cudaSuccess) { rcs[g] = GRT_E_CUDA; errs[g] = cudaGetErrorString(e); return; }
-            rcs[g] = grt_render_device(hs[g], cam, &o, fused ? d_shared : d_sum[g], st[g], nullptr);
+            rcs[g] = grt_render_device(hs[g], cam, &o, direct ? d_shared : d_sum[g], st[g], nullptr);
+            if (!rcs[g] && fused && !direct) rcs[g] = grt_internal_peer_accumulate(d_shared, d_sum[g], nval, st[g]);
             if (rcs[g]) errs[g] = grt_last_error();   // the error text is thread-local: carry it to the caller
         };
         if (n == 1) work(0);
@@ -184,7 +208,6 @@ extern "C" int grt_render_multi(const GrtScene* scene, const GrtCamera* cam, con
 done:
     for (int g = 0; g < n; g++) {
         if (hs[g]) cudaSetDevice(devices[g]);
-        if (comms_ok && comms[g]) g_nccl.CommDestroy(comms[g]);
         if (d_sum[g]) grt_dev_free(d_sum[g]);
         if (e0[g]) cudaEventDestroy(e0[g]);
         if (e1[g]) cudaEventDestroy(e1[g]);
