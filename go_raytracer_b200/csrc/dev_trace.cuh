@@ -586,32 +586,66 @@ __device__ __forceinline__ bool trav_run(const SceneView& sv, TS& ts, const RayD
         return type == GRT_REF_QUAD || type == GRT_REF_SPHERE || type == GRT_REF_TRI || type == GRT_REF_BOX || type == GRT_REF_NONE;
     };
 
-    // one item that is not an inner node: a list (scanned in order), a medium, or a primitive
+    // One item that is not an inner node: a run of primitives named by its parent node, a list (scanned in order), a
+    // medium, or a single primitive.  How the primitive runs reach test_prims depends on the variant, and both shapes are
+    // measured (profiles/README.md, round 2):
+    //  * variants with a BVH or media: ONE call site, inside a loop.  With several, nvcc outlines the lambda in the
+    //    all-feature variants and everything it captures by reference (the ray, the scene view, the closest hit) lives
+    //    in local memory for the whole kernel (book 2: 560 -> 636 Mpaths/s once it stayed inline; smoke 4620 -> 5290).
+    //  * the surface-only list variant (the Cornell box): the list scan with its own call site plus one for a bare
+    //    primitive; funnelling both through one loop costs the unrolled 6-quad run its straight-line schedule
+    //    (9400 -> 7770).
     auto leaf = [&](uint32_t ref) {
-        if ((FEAT & F_NODE) && (ref & GRT_DREF_RUN_BIT)) {   // a leaf run named by its parent node: (type, count, first index)
-            test_prims((ref & (7u << GRT_REF_SHIFT)) | (ref & GRT_DREF_RUN_INDEX_MASK), ((ref >> 25) & 7u) + 1u);
-            return;
-        }
-        uint32_t type = GRT_REF_TYPE(ref);
-        uint32_t idx = ref & GRT_REF_MASK;
-        if ((FEAT & F_LIST) && type == GRT_REF_LIST) {
-            const uint2* entries = sv.entries();
-            for (;;) {
-                const uint2 e = entries[idx];
-                const bool last = (e.x & GRT_LIST_LAST) != 0;
-                ref = e.x & ~GRT_LIST_LAST;
-                if (test_prims(ref, e.y)) {
-                    if (last) { ref = GRT_MAKE_REF(GRT_REF_NONE, 0); break; }
-                    idx++;
-                    continue;
-                }
-                if (!last) ts.put(sp++, GRT_MAKE_REF(GRT_REF_LIST, idx + 1));   // the rest of the list, after this item
-                break;
+        uint32_t type, idx;
+        if constexpr ((FEAT & (F_NODE | F_MEDIUM)) != 0) {
+            uint32_t pref = ref, cnt = 1u, lidx = 0u;
+            bool in_list = false, last = true;
+            if ((FEAT & F_NODE) && (ref & GRT_DREF_RUN_BIT)) {   // (type, count, first index) packed by wide_bvh.hpp
+                pref = (ref & (7u << GRT_REF_SHIFT)) | (ref & GRT_DREF_RUN_INDEX_MASK);
+                cnt = ((ref >> 25) & 7u) + 1u;
+            } else if ((FEAT & F_LIST) && GRT_REF_TYPE(ref) == GRT_REF_LIST) {
+                in_list = true;
+                lidx = ref & GRT_REF_MASK;
             }
+            for (;;) {
+                if ((FEAT & F_LIST) && in_list) {
+                    const uint2 e = sv.entries()[lidx];
+                    last = (e.x & GRT_LIST_LAST) != 0;
+                    pref = e.x & ~GRT_LIST_LAST;
+                    cnt = e.y;
+                }
+                if (!test_prims(pref, cnt)) break;        // not a primitive type: handled below
+                if (!in_list || last) return;
+                lidx++;
+            }
+            if (in_list && !last) ts.put(sp++, GRT_MAKE_REF(GRT_REF_LIST, lidx + 1));   // the rest of the list, after this item
+            ref = pref;
             type = GRT_REF_TYPE(ref);
             idx = ref & GRT_REF_MASK;
             if (type == GRT_REF_LIST || type == GRT_REF_NODE) { ts.put(sp++, ref); return; }   // nested list / a BVH inside a list: next pop
-            if (type == GRT_REF_NONE) return;
+        } else {
+            type = GRT_REF_TYPE(ref);
+            idx = ref & GRT_REF_MASK;
+            if ((FEAT & F_LIST) && type == GRT_REF_LIST) {
+                const uint2* entries = sv.entries();
+                for (;;) {
+                    const uint2 e = entries[idx];
+                    const bool last = (e.x & GRT_LIST_LAST) != 0;
+                    ref = e.x & ~GRT_LIST_LAST;
+                    if (test_prims(ref, e.y)) {
+                        if (last) { ref = GRT_MAKE_REF(GRT_REF_NONE, 0); break; }
+                        idx++;
+                        continue;
+                    }
+                    if (!last) ts.put(sp++, GRT_MAKE_REF(GRT_REF_LIST, idx + 1));   // the rest of the list, after this item
+                    break;
+                }
+                type = GRT_REF_TYPE(ref);
+                idx = ref & GRT_REF_MASK;
+                if (type == GRT_REF_LIST || type == GRT_REF_NODE) { ts.put(sp++, ref); return; }   // nested list: next pop
+                if (type == GRT_REF_NONE) return;
+            }
+            if (type != GRT_REF_MEDIUM) { test_prims(ref, 1); return; }   // a bare primitive, or NONE
         }
         if (!BOUNDARY && (FEAT & F_MEDIUM) && type == GRT_REF_MEDIUM) {
             // constantMedium.Hit, medium.go:27-58
@@ -637,8 +671,14 @@ __device__ __forceinline__ bool trav_run(const SceneView& sv, TS& ts, const RayD
                 if (box_prim_pick(bs, -INF, INF, -1, h1.t, nt) < 0) return;
                 if (box_prim_pick(bs, h1.t + 0.0001f, INF, -1, h2.t, nt) < 0) return;
             } else {
-                if (!closest_hit<FEAT, true, STATS>(sv, m.boundary, r, -INF, INF, GRT_NO_ID, 0xFFFFFFFFu, nullptr, h1, tc)) return;
-                if (!closest_hit<FEAT, true, STATS>(sv, m.boundary, r, h1.t + 0.0001f, INF, GRT_NO_ID, 0xFFFFFFFFu, nullptr, h2, tc)) return;
+                // A general boundary (a BVH or list): two nested queries through closest_hit, which is a real function call
+                // here.  It gets COPIES of the view and the ray: handing it references to `sv` and `r` forces both into
+                // local memory for the whole kernel — on the book-2 cover, whose boundaries never take this path, the
+                // extend kernel read every ray component with LDL (153 M local vs 69 M global load sectors per launch).
+                const SceneView svb = sv;
+                const RayD rb = r;
+                if (!closest_hit<FEAT, true, STATS>(svb, m.boundary, rb, -INF, INF, GRT_NO_ID, 0xFFFFFFFFu, nullptr, h1, tc)) return;
+                if (!closest_hit<FEAT, true, STATS>(svb, m.boundary, rb, h1.t + 0.0001f, INF, GRT_NO_ID, 0xFFFFFFFFu, nullptr, h2, tc)) return;
             }
             float t1 = fmaxf(h1.t, tmin), t2 = fminf(h2.t, tmax);
             if (t1 >= t2) return;
@@ -653,7 +693,6 @@ __device__ __forceinline__ bool trav_run(const SceneView& sv, TS& ts, const RayD
             tmax = t; hit.ref = ref; hit.u = 0; hit.v = 0;
             return;
         }
-        test_prims(ref, 1);   // a primitive that is a direct BVH child (bvh.go:73,79), or NONE
     };
     // one inner node: four slab tests, then the nearest hit child (or, under a medium, the first in the reference's
     // order) becomes current and the other hit children wait on the stack, nearest on top
