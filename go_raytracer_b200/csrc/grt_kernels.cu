@@ -550,6 +550,13 @@ static int repack_scene(const GrtScene* s, Repacked& R) {
     // the 4-wide BVH (wide_bvh.hpp): NODE refs held by lists, media and the root now index the wide array
     grt::wide::Builder wb(s, nodes, entries, R.media);
     if (!wb.run(remap(s->root), R.wide)) { grt_set_error("wide BVH build: " + R.wide.error); return GRT_E_UNSUPPORTED; }
+    if (wb.sah && (R.wide.need_main > GRT_STACK_MAIN || R.wide.need_boundary > GRT_STACK_BOUNDARY)) {
+        // a regrouped tree may be arbitrarily unbalanced; BuildBVH's median splits are not
+        grt::wide::Builder plain(s, nodes, entries, R.media);
+        plain.sah = 0;
+        R.wide = grt::wide::Result();
+        if (!plain.run(remap(s->root), R.wide)) { grt_set_error("wide BVH build: " + R.wide.error); return GRT_E_UNSUPPORTED; }
+    }
     if (R.wide.need_main > GRT_STACK_MAIN || R.wide.need_boundary > GRT_STACK_BOUNDARY) {
         grt_set_error("scene needs a deeper traversal stack than the kernels provide");
         return GRT_E_UNSUPPORTED;

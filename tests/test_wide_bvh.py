@@ -105,6 +105,14 @@ def binary_prims(ref, A, out):
 SCENES = [(1, {}), (2, {}), (3, {}), (6, {}), (7, {}), (8, {"mesh_segments": 24})]
 
 
+@pytest.fixture(autouse=True, params=["sah", "plain"])
+def tree_build(request, monkeypatch):
+    """Every test runs on both trees the upload can build: medium-free subtrees regrouped by the surface area heuristic
+    (the default) and BuildBVH's own topology, only widened (GRT_WIDE_SAH=0)."""
+    monkeypatch.setenv("GRT_WIDE_SAH", "1" if request.param == "sah" else "0")
+    return request.param
+
+
 @pytest.mark.parametrize("sid,kw", SCENES)
 def test_wide_tree_holds_exactly_the_binary_trees_primitives(sid, kw):
     s, cfg = g.builtin_scene(sid, width=64, spp=1, **kw)
@@ -253,3 +261,77 @@ def test_culling_never_loses_the_oracles_hit(sid, kw):
         checked += 1
     assert checked > 50
     assert deepest_all <= R["need_main"], (deepest_all, R["need_main"])
+
+
+def _inner_area(R):
+    """Sum of the box areas of all inner-node children below the huge ones (ground sphere, world list): proportional to
+    the node visits of a random ray."""
+    wn = R["wnodes"]
+    lo = wn[:, 0:12].reshape(-1, 3, 4).astype(np.float64)
+    hi = wn[:, 12:24].reshape(-1, 3, 4).astype(np.float64)
+    ref = wn[:, 24:28].copy().view(np.uint32)
+    cnt = wn[:, 29].copy().view(np.uint32)
+    e = np.clip(hi - lo, 0, None)
+    area = e[:, 0] * e[:, 1] + e[:, 1] * e[:, 2] + e[:, 2] * e[:, 0]
+    valid = (np.arange(4)[None, :] < cnt[:, None]) & np.isfinite(area)
+    area = np.where(valid, area, 0.0)
+    inner = valid & ((ref >> 31) == 0) & (area < 0.01 * area.max())
+    return area[inner].sum()
+
+
+@pytest.mark.parametrize("sid,kw", [(1, {}), (8, {"mesh_segments": 64})])
+def test_sah_regrouping_lowers_the_expected_node_visits(sid, kw, monkeypatch, tree_build):
+    if tree_build != "sah":
+        pytest.skip("compares the two builds itself")
+    s, cfg = g.builtin_scene(sid, width=64, spp=1, **kw)
+    flat = s.flatten()
+    monkeypatch.setenv("GRT_WIDE_SAH", "0")
+    plain = repack(flat)
+    monkeypatch.setenv("GRT_WIDE_SAH", "1")
+    sah = repack(flat)
+    assert len(sah["wnodes"]) <= len(plain["wnodes"])
+    assert _inner_area(sah) < 0.9 * _inner_area(plain), (_inner_area(sah), _inner_area(plain))
+    assert sah["need_main"] <= 64
+
+
+def test_subtrees_with_a_medium_keep_the_references_order(monkeypatch, tree_build):
+    """Book 2 holds two constant media in its world list: whatever lies on a path from the root to a medium must keep
+    BuildBVH's / the list's child order (a medium test draws a random number, medium.go:47), so those nodes are
+    identical in both builds and are flagged in-order (meta bit 0 clear)."""
+    if tree_build != "sah":
+        pytest.skip("compares the two builds itself")
+    s, cfg = g.builtin_scene(2, width=64, spp=1, image=np.zeros((2, 2, 3), np.uint8))
+    flat = s.flatten()
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("GRT_WIDE_SAH", mode)
+        R = repack(flat)
+        # walk down from the root through every child whose subtree reaches a medium; record (depth, child slot, ordered flag)
+        trail = []
+
+        def has_medium(ref):
+            ref = int(ref)
+            if ref & RUN_BIT:
+                return False
+            t, i = rtype(ref), ref & N.REF_MASK
+            if t == N.REF_MEDIUM:
+                return True
+            if t == N.REF_NODE:
+                lo, hi, refs, meta = node_fields(R["wnodes"][i])
+                return any(has_medium(refs[k]) for k in range(int(meta[1])))
+            return False
+
+        def walk(ref, depth):
+            i = int(ref) & N.REF_MASK
+            lo, hi, refs, meta = node_fields(R["wnodes"][i])
+            kids = [int(refs[k]) for k in range(int(meta[1]))]
+            trail.append((depth, int(meta[0]) & 1, [rtype(k) if not (k & RUN_BIT) else -1 for k in kids], [tuple(np.round(lo[k], 3)) for k in range(len(kids))]))
+            for k in kids:
+                if not (k & RUN_BIT) and rtype(k) == N.REF_NODE and has_medium(k):
+                    walk(k, depth + 1)
+
+        assert has_medium(R["root"])
+        walk(R["root"], 0)
+        assert all(flag == 0 for _, flag, _, _ in trail), "a node above a medium is flagged nearest-first"
+        out[mode] = trail
+    assert out["0"] == out["1"]
