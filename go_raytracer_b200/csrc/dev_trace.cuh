@@ -498,7 +498,7 @@ __device__ bool closest_hit(const SceneView& sv, uint32_t root, const RayD& r, f
 template <uint32_t FEAT, bool BOUNDARY, bool STATS, bool VOTE, typename TS>
 __device__ __forceinline__ bool trav_run(const SceneView& sv, TS& ts, const RayD& r, float tmin,
                                          uint32_t self_id, uint32_t self_ref, MediumRngCtx* mrng, TraceCounters* tc,
-                                         unsigned mask, int exit16) {
+                                         unsigned mask, int exit16, int vote16 = 8) {
     int sp = ts.sp;
     float tmax = ts.tmax;
     HitInfo hit;
@@ -796,7 +796,9 @@ __device__ __forceinline__ bool trav_run(const SceneView& sv, TS& ts, const RayD
     } else {
         // Warp-synchronous traversal.  The lanes in `mask` (they all enter together) vote on every step: while at
         // least half of the lanes that still have work stand on an inner node, those lanes do one box test each in
-        // lock step; otherwise the lanes standing on a leaf item (list, medium, primitive) process it.  Left to the
+        // lock step (vote16/16 instead of half: where the leaves are expensive — fp64 sphere tests, box slabs, media — it
+        // pays to let more lanes gather on leaves first, 4/16; on triangle meshes half is best; measured, profiles/README.md);
+        // otherwise the lanes standing on a leaf item (list, medium, primitive) process it.  Left to the
         // compiler's reconvergence the lanes of a warp drift apart and run the loop almost serially (measured:
         // 5 of 32 lanes active per instruction on the 1M-triangle mesh).  The slice ends for the whole warp once
         // fewer than exit16/16 of the entering lanes still have work: those keep their state and resume on the
@@ -811,7 +813,7 @@ __device__ __forceinline__ bool trav_run(const SceneView& sv, TS& ts, const RayD
             const int n_have = __popc(__ballot_sync(mask, have));
             const int n_node = __popc(__ballot_sync(mask, on_node));
             if (n_have * 16 < n_enter * exit16 || n_have == 0) break;
-            if (2 * n_node >= n_have) {
+            if (16 * n_node >= vote16 * n_have) {
                 if (on_node) node_step(ref);
             } else if (have && !on_node) {
                 leaf(ref);

@@ -52,6 +52,7 @@ struct WfParams {
     float* rgb_sum;
     int sys_atomics;                  // rgb_sum may live on a peer GPU (grt_render_multi): system-scope atomics
     int exit16;                       // wf_extend_dyn: a traversal slice ends when fewer than exit16/16 lanes have work
+    int vote16;                       // wf_extend_dyn: a node step runs while at least vote16/16 of the lanes with work stand on an inner node
     uint32_t treelet_nodes;           // wf_extend_dyn<.., TREELET>: wide nodes staged in shared memory per block
 };
 
@@ -250,7 +251,7 @@ __global__ void __launch_bounds__(WF_DYN_THREADS, WF_DYN_MIN_BLOCKS) wf_extend_d
         if (!__any_sync(FULL, have)) { if (exhausted) break; else continue; }
         MediumRngCtx mr;
         mr.pixel = s3.x; mr.sample = s3.y; mr.bounce = s3.z & 255u; mr.k0 = P.k0; mr.k1 = P.k1; mr.count = med_count;
-        const bool fin = trav_run<TF, false, false, true>(sv, ts, ray, 0.001f, s3.w, self_ref, &mr, nullptr, FULL, P.exit16);
+        const bool fin = trav_run<TF, false, false, true>(sv, ts, ray, 0.001f, s3.w, self_ref, &mr, nullptr, FULL, P.exit16, P.vote16);
         med_count = mr.count;
         if (have && fin) {
             HitInfo h;
@@ -370,8 +371,11 @@ static int wf_run(GrtSceneHandle h, WfParams& P, cudaStream_t st, uint32_t* h_co
     // BVH, one primitive per leaf and lists as wide nodes (profiles/README.md, round 2): triangle meshes 462 vs 232
     // Mpaths/s, the sphere BVH of book 1 796 vs 696, the book-2 cover 538 vs 510 — every BVH scene takes the persistent
     // kernel now (round 1's binary tree with 4-primitive leaves had book 2 the other way round: 252 vs 311).
+    // Since the medium-free subtrees are regrouped by SAH (wide_bvh.hpp) book 1 visits ~7 nodes of a 140-node tree per ray:
+    // that small a scene sits in shared memory whole and the plain kernel wins again (1662 vs 1547), book 2 (521 nodes, two
+    // media) stays with the persistent one (743 vs 657).
     constexpr bool can_dyn = (FEAT & F_NODE) != 0;
-    bool dyn = can_dyn;
+    bool dyn = can_dyn && !(P.scene.n_nodes < 256u && P.scene.n_media == 0u);
     if (const char* e = getenv("GRT_WF_DYN")) dyn = can_dyn && (atoi(e) == 2 || (dyn && atoi(e) != 0));   // 0: never, 2: whenever compiled in
     const bool staged = grt_internal_staged(h) == 2 && !dyn;   // whole-blob staging or none
     {
@@ -545,8 +549,18 @@ int grt_render_wavefront(GrtSceneHandle h, const GrtCamera* cam, const GrtOption
     P.P = (uint32_t)((want + 255) / 256 * 256);
     P.rgb_sum = d_rgb_sum;
     P.sys_atomics = (opt->flags & GRT_OPT_ATOMIC_SUM) ? 1 : 0;
-    P.exit16 = 12;
+    // Slice exit: the warp leaves a traversal slice (to flush finished rays and fetch new ones) once fewer than exit16/16
+    // of the lanes that entered still have work.  A refill costs a pass of atomics, ray fetches and stack resets, so it
+    // only pays where traversal lengths differ a lot: the 1M-triangle mesh 9/16 (2 / 4 / 6 / 8 / 9 / 10 / 12: 445 / 484 /
+    // 509 / 518 / 522 / 519 / 497 Mpaths/s), book 2 with its media 3/16 (0 / 2 / 3 / 4 / 8 / 12: 718 / 737 / 743 / 745 /
+    // 720 / 658), book 1's 140-node tree runs every ray of the warp to its end (0 / 2 / 4 / 8 / 12: 1544 / 1470 / 1409 /
+    // 1303 / 1079).
+    P.exit16 = P.scene.n_nodes >= WF_DYN_TREELET_MIN_NODES ? 9 : (P.scene.n_media ? 3 : 0);
     if (const char* e = getenv("GRT_WF_EXIT16")) { int v = atoi(e); if (v >= 0 && v <= 16) P.exit16 = v; }
+    // node-step quorum: triangle meshes 8/16, scenes whose leaves are spheres / boxes / media 2/16
+    // (8 / 4 / 2 sixteenths: mesh 500 / 478 / -, book 2 634 / 653 / 660, book 1 994 / 1059 / 1070 Mpaths/s)
+    P.vote16 = (P.scene.n_tris > P.scene.n_spheres + P.scene.n_boxes) ? 10 : 2;
+    if (const char* e = getenv("GRT_WF_VOTE16")) { int v = atoi(e); if (v >= 1 && v <= 16) P.vote16 = v; }
     void* pool = nullptr;
     uint32_t* h_counters = nullptr;
     const bool timing = (opt->flags & GRT_OPT_TIMING) != 0;
