@@ -163,7 +163,8 @@ __global__ void __launch_bounds__(256, WF_EXT_MIN_BLOCKS) wf_extend(const __grid
 // unlike the megakernel nothing ties a lane to a pixel.
 #define WF_DYN_THREADS 128
 #ifndef WF_DYN_TREELET
-#define WF_DYN_TREELET 32         /* wide nodes (128 B each) staged in shared memory per block for trees of at least ... */
+#define WF_DYN_TREELET 0          /* wide nodes (128 B each) staged in shared memory per block for trees of at least ... (0: off — with the
+                                     SAH-regrouped tree 0 / 32 / 64 nodes measure 544 / 531 / 526 Mpaths/s on the mesh; GRT_WF_TREELET=n turns it on) */
 #endif
 #ifndef WF_DYN_TREELET_MIN_NODES
 #define WF_DYN_TREELET_MIN_NODES 16384u   /* ... this many wide nodes (smaller trees are L1-resident: staging only shrinks the L1) */
