@@ -235,7 +235,7 @@ def measure_config(name, spp, steps, warmup, local, seed, cores, want_cpu, peaks
     torch.cuda.synchronize()
     T = last_timing(L)
     share = T.extend_ms / T.total_ms if T.total_ms > 0 else None
-    dominant = "render_mega_kernel" if variant == "megakernel" else "wf_extend_dyn"    # every BVH scene takes the persistent extend
+    dominant = ("render_mega_kernel", "wf_extend", "wf_extend_dyn")[int(T.extend_kernel)]    # the library picks per scene (grt_wavefront.cu)
     scene.close()
     cpu, ev, ev_src = None, None, None
     if want_cpu:
@@ -526,7 +526,8 @@ def run_ours(args):
             except Exception:
                 pass
             bind = rp["fp32"] if rp["bound"] == "fp32_issue" else rp["bytes"]
-            roofline = {"kernel": "render_mega_kernel" if vname == "mega" else "wf_extend_dyn (the wavefront variant's traversal + intersection kernel)",
+            roofline = {"kernel": ("render_mega_kernel", "wf_extend (the wavefront variant's traversal + intersection kernel, one thread per slot)",
+                                   "wf_extend_dyn (the wavefront variant's traversal + intersection kernel, persistent warps)")[int(T.extend_kernel)],
                         "bound": rp["bound"], "achieved": bind["achieved"], "peak": bind["peak"], "unit": bind["unit"], "frac": bind["frac"],
                         "peak_source": bind["peak_source"], "kernel_ms_per_step": T.extend_ms, "kernel_share_of_step": dom_share,
                         "kernel_launches_per_step": int(T.extend_launches),

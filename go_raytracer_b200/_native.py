@@ -74,7 +74,7 @@ class GrtStats(C.Structure):
 class GrtTiming(C.Structure):
     """grt_last_timing: device time per kernel class of the last GRT_OPT_TIMING render (CUDA events)."""
     _fields_ = [("total_ms", C.c_double), ("generate_ms", C.c_double), ("extend_ms", C.c_double), ("shade_ms", C.c_double),
-                ("extend_launches", C.c_uint64), ("launches", C.c_uint64)]
+                ("extend_launches", C.c_uint64), ("launches", C.c_uint64), ("extend_kernel", C.c_uint64)]
 
 
 class GrtScene(C.Structure):

@@ -505,6 +505,7 @@ static int wf_run(GrtSceneHandle h, WfParams& P, cudaStream_t st, uint32_t* h_co
         }
         if (tev.size() >= 4) { float t = 0; cudaEventElapsedTime(&t, tev.front(), tev.back()); T.total_ms = t; }
         T.launches = launches;
+        T.extend_kernel = dyn ? 2u : 1u;
         grt_internal_set_timing(T);
     }
 done:

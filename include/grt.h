@@ -340,6 +340,8 @@ typedef struct GrtTiming {
     double   shade_ms;               /* BSDF scatter, PDF mixture, clamp unwind, accumulation             */
     uint64_t extend_launches;
     uint64_t launches;
+    uint64_t extend_kernel;          /* which kernel `extend_ms` timed: 0 render_mega_kernel, 1 wf_extend (one thread per
+                                        slot), 2 wf_extend_dyn (persistent warps) — the library picks per scene         */
 } GrtTiming;
 int grt_last_timing(GrtTiming* out);
 
