@@ -183,6 +183,22 @@ def scene_bytes(flat):
             flat.n_media * 16 + flat.n_materials * 32 + flat.n_textures * 32 + flat.n_lights * 304 + int(flat.n_texel_bytes))
 
 
+class stdout_to_stderr:
+    """File-descriptor level: whatever native libraries print to stdout inside (NCCL's version banner when NCCL_DEBUG
+    is set in the environment) goes to stderr, so that stdout stays the ONE JSON line of the contract."""
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
 def last_timing(L):
     from go_raytracer_b200 import _native as N
     t = N.GrtTiming()
@@ -302,17 +318,18 @@ def run_inproc(args):
     out = {}
     for mode in (["1", "0"] if n > 1 else ["1"]):
         os.environ["GRT_MULTI_P2P"] = mode
-        for _ in range(max(1, args.warmup // 2)):
-            sums[:] = 0
-            N.check(L.grt_render_multi(C.byref(flat), C.byref(cam), C.byref(opt), devs, n, sums.ctypes.data, rgb8.ctypes.data, C.byref(kms)))
-        t_dev, t_wall = 0.0, 0.0
-        l0 = L.grt_launch_count()
-        for _ in range(args.steps):
-            sums[:] = 0
-            t0 = time.perf_counter()
-            N.check(L.grt_render_multi(C.byref(flat), C.byref(cam), C.byref(opt), devs, n, sums.ctypes.data, rgb8.ctypes.data, C.byref(kms)))
-            t_wall += time.perf_counter() - t0
-            t_dev += kms.value
+        with stdout_to_stderr():
+            for _ in range(max(1, args.warmup // 2)):
+                sums[:] = 0
+                N.check(L.grt_render_multi(C.byref(flat), C.byref(cam), C.byref(opt), devs, n, sums.ctypes.data, rgb8.ctypes.data, C.byref(kms)))
+            t_dev, t_wall = 0.0, 0.0
+            l0 = L.grt_launch_count()
+            for _ in range(args.steps):
+                sums[:] = 0
+                t0 = time.perf_counter()
+                N.check(L.grt_render_multi(C.byref(flat), C.byref(cam), C.byref(opt), devs, n, sums.ctypes.data, rgb8.ctypes.data, C.byref(kms)))
+                t_wall += time.perf_counter() - t0
+                t_dev += kms.value
         out["fused_peer_atomics" if mode == "1" else "nccl_reduce"] = {
             "value": paths * args.steps / (t_dev / 1e3) / 1e6, "device_ms_per_step": t_dev / args.steps,
             "e2e_value": paths * args.steps / t_wall / 1e6, "wall_ms_per_step": 1e3 * t_wall / args.steps,
@@ -465,11 +482,12 @@ def run_ours(args):
                 hs = np.zeros(nval, dtype=np.float32)
                 kms = C.c_double(0)
                 os.environ["GRT_MULTI_P2P"] = "1"
-                N.check(L.grt_render_multi(C.byref(flat), C.byref(cam), C.byref(opt), devs, world, hs.ctypes.data, None, C.byref(kms)))
-                hs[:] = 0
-                tw = time.perf_counter()
-                N.check(L.grt_render_multi(C.byref(flat), C.byref(cam), C.byref(opt), devs, world, hs.ctypes.data, None, C.byref(kms)))
-                tw = time.perf_counter() - tw
+                with stdout_to_stderr():
+                    N.check(L.grt_render_multi(C.byref(flat), C.byref(cam), C.byref(opt), devs, world, hs.ctypes.data, None, C.byref(kms)))
+                    hs[:] = 0
+                    tw = time.perf_counter()
+                    N.check(L.grt_render_multi(C.byref(flat), C.byref(cam), C.byref(opt), devs, world, hs.ctypes.data, None, C.byref(kms)))
+                    tw = time.perf_counter() - tw
                 inproc = {"what": f"grt_render_multi on {world} GPUs from ONE process (rank 0; fused NVLink peer-atomic accumulation when available), one call",
                           "value": paths / (kms.value / 1e3) / 1e6, "device_ms": kms.value, "e2e_value": paths / tw / 1e6, "wall_ms": 1e3 * tw,
                           "mean": float(hs.mean() / S2)}

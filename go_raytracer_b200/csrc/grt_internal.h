@@ -47,5 +47,5 @@ void grt_dev_free(void* p);
 void* grt_internal_wf_pool(GrtSceneHandle h, size_t bytes, void** pinned64);
 void grt_internal_set_timing(const GrtTiming& t);
 int grt_internal_resolve_variant(GrtSceneHandle h, const GrtOptions* opt, bool has_stats_buffer);   /* what GRT_VARIANT_AUTO picks */
-int grt_internal_peer_accumulate(float* d_dst, const float* d_src, uint64_t n, cudaStream_t st);
+int grt_internal_peer_pull(float* d_dst, const float* d_src, uint64_t n, cudaStream_t st);
 int grt_make_dev_camera(const GrtCamera* c, grtd::DevCamera* out);

@@ -7,8 +7,10 @@
 // atomics as each pixel is retired — the exchange is spread over the whole render (12.6 MB of 4-byte reductions over
 // tens of milliseconds) instead of following it, and no collective runs at all.  That holds for the megakernel, which
 // retires one sum per PIXEL.  The wavefront kernels retire one sum per PATH (paths of a pixel are spread over the pool),
-// and a remote atomic per path is 10^8 NVLink transactions per frame: there a peer device accumulates into a private
-// buffer at home and adds that buffer into the shared one once, at the end, with one system-scope atomic per value.
+// and a remote atomic per path is 10^8 NVLink transactions per frame: there every device accumulates at home (plain
+// device-scope atomics), and devices[0] PULLS each peer's finished buffer over NVLink with coalesced 128-bit peer loads
+// and adds it to its own (peer_pull_kernel, ~0.2 ms for a 100 MB frame; the pool memory of the peers is opened to
+// devices[0] with cudaMemPoolSetAccess).
 // Fallback (no peer access): private buffers and ONE ncclReduce(sum, root = devices[0]) before tonemap.
 // The devices render concurrently (one host thread each); kernel_ms is the slowest device's e0..e1 time.
 // (bench.py instead runs one process per GPU and reduces through torch.distributed's NCCL communicator.)
@@ -65,6 +67,39 @@ Nccl g_nccl;
         if (r_ != 0) { grt_set_error(std::string(#call) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "nccl error")); rc = GRT_E_NCCL; goto done; } \
     } while (0)
 
+// One plain-cudaMalloc buffer per device, kept for the life of the process (cudaFree costs 30-500 ms once a process
+// holds a few GB); a second concurrent caller gets a fresh allocation of its own.
+namespace {
+struct PeerBuf { float* p = nullptr; size_t bytes = 0; bool busy = false; };
+std::mutex g_peer_m;
+PeerBuf g_peer_buf[64];
+float* peer_buf_acquire(int dev, size_t bytes, int* own) {
+    *own = 0;
+    if (cudaSetDevice(dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lk(g_peer_m);
+    if (dev >= 0 && dev < 64 && !g_peer_buf[dev].busy) {
+        PeerBuf& b = g_peer_buf[dev];
+        if (b.bytes < bytes) {
+            if (b.p) cudaFree(b.p);
+            b.p = nullptr; b.bytes = 0;
+            if (cudaMalloc((void**)&b.p, bytes) != cudaSuccess) { cudaGetLastError(); b.p = nullptr; return nullptr; }
+            b.bytes = bytes;
+        }
+        b.busy = true; *own = 1;
+        return b.p;
+    }
+    float* p = nullptr;
+    if (cudaMalloc((void**)&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    *own = 2;
+    return p;
+}
+void peer_buf_release(int dev, float* p, int own) {
+    if (own == 2) { cudaSetDevice(dev); cudaFree(p); return; }
+    std::lock_guard<std::mutex> lk(g_peer_m);
+    if (dev >= 0 && dev < 64 && g_peer_buf[dev].p == p) g_peer_buf[dev].busy = false;
+}
+}   // namespace
+
 extern "C" int grt_render_multi(const GrtScene* scene, const GrtCamera* cam, const GrtOptions* opt, const int* devices, int n,
                                 float* rgb_sum, uint8_t* rgb8, double* kernel_ms) {
     if (!scene || !cam || !opt || !devices || n < 1 || !rgb_sum) { grt_set_error("grt_render_multi: bad argument"); return GRT_E_INVALID; }
@@ -79,6 +114,7 @@ extern "C" int grt_render_multi(const GrtScene* scene, const GrtCamera* cam, con
         if (devices[g] == devices[0]) { fused = false; break; }
         if (cudaDeviceCanAccessPeer(&can, devices[g], devices[0]) != cudaSuccess || !can) fused = false;
         else if (cudaDeviceGetP2PAttribute(&at, cudaDevP2PAttrNativeAtomicSupported, devices[g], devices[0]) != cudaSuccess || !at) fused = false;
+        else if (cudaDeviceCanAccessPeer(&can, devices[0], devices[g]) != cudaSuccess || !can) fused = false;   // (the pull direction)
     }
     if (n > 1 && !fused && !g_nccl.load()) { grt_set_error("libnccl.so.2 could not be loaded"); return GRT_E_NCCL; }
 
@@ -93,6 +129,8 @@ extern "C" int grt_render_multi(const GrtScene* scene, const GrtCamera* cam, con
     float* d_shared = nullptr;      // fused path: the one accumulation buffer, plain cudaMalloc (peer-mappable) on devices[0]
     cudaEvent_t e_init = nullptr;
     float* d_total = nullptr;       // where the complete sums end up (on devices[0])
+    bool wf = false;                // fused path, wavefront shards: private sums, pulled by devices[0] at the end
+    std::vector<int> own_sum(n, 0); // d_sum[g] came from peer_buf_acquire: 1 = the kept buffer of that device, 2 = a fresh cudaMalloc
 
     for (int g = 0; g < n; g++) {
         rc = grt_scene_upload(scene, devices[g], &hs[g]);
@@ -102,9 +140,19 @@ extern "C" int grt_render_multi(const GrtScene* scene, const GrtCamera* cam, con
         CU(cudaEventCreate(&e0[g]));
         CU(cudaEventCreate(&e1[g]));
         if (fused) {
-            if (g > 0 && grt_internal_resolve_variant(hs[g], opt, false) == GRT_VARIANT_WAVEFRONT) {
-                CU(grt_dev_alloc((void**)&d_sum[g], nval * sizeof(float)));     // private sums, added to the shared buffer at the end
+            if (g == 0) wf = grt_internal_resolve_variant(hs[0], opt, false) == GRT_VARIANT_WAVEFRONT;
+            if (g > 0 && wf) {
+                // private sums, pulled into the shared buffer at the end: plain cudaMalloc memory (peer-mappable; opening
+                // the stream-ordered pool to devices[0] with cudaMemPoolSetAccess made the NEXT big pool allocation of
+                // this device fail with "out of memory" on these boxes), kept per device across calls
+                d_sum[g] = peer_buf_acquire(devices[g], nval * sizeof(float), &own_sum[g]);
+                if (!d_sum[g]) { grt_set_error("grt_render_multi: cannot allocate the private accumulation buffer"); rc = GRT_E_CUDA; goto done; }
                 CU(cudaMemsetAsync(d_sum[g], 0, nval * sizeof(float), st[g]));
+                CU(cudaSetDevice(devices[0]));
+                cudaError_t pe = cudaDeviceEnablePeerAccess(devices[g], 0);
+                if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) { grt_set_error(std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(pe)); rc = GRT_E_CUDA; goto done; }
+                cudaGetLastError();
+                CU(cudaSetDevice(devices[g]));
             }
             if (g == 0) {
                 CU(cudaMalloc((void**)&d_shared, nval * sizeof(float)));
@@ -153,12 +201,11 @@ extern "C" int grt_render_multi(const GrtScene* scene, const GrtCamera* cam, con
             o.sample_stride = base_stride * (uint32_t)n;
             o.device = devices[g];
             const bool direct = fused && !d_sum[g];   // this shard adds straight into the shared buffer as it goes
-            if (direct) o.flags |= GRT_OPT_ATOMIC_SUM;
+            if (direct && !wf) o.flags |= GRT_OPT_ATOMIC_SUM;   // (wavefront: devices[0] is alone on the shared buffer until the pull)
             cudaError_t e = cudaSetDevice(devices[g]);
             if (e == cudaSuccess) e = cudaEventRecord(e0[g], st[g]);
             if (e != cudaSuccess) { rcs[g] = GRT_E_CUDA; errs[g] = cudaGetErrorString(e); return; }
             rcs[g] = grt_render_device(hs[g], cam, &o, direct ? d_shared : d_sum[g], st[g], nullptr);
-            if (!rcs[g] && fused && !direct) rcs[g] = grt_internal_peer_accumulate(d_shared, d_sum[g], nval, st[g]);
             if (rcs[g]) errs[g] = grt_last_error();   // the error text is thread-local: carry it to the caller
         };
         if (n == 1) work(0);
@@ -177,12 +224,16 @@ extern "C" int grt_render_multi(const GrtScene* scene, const GrtCamera* cam, con
         }
         NC(g_nccl.GroupEnd());
     }
-    for (int g = 0; g < n; g++) {
+    for (int g = 1; g < n; g++) {
         CU(cudaSetDevice(devices[g]));
         CU(cudaEventRecord(e1[g], st[g]));
     }
     CU(cudaSetDevice(devices[0]));
-    if (fused) for (int g = 1; g < n; g++) CU(cudaStreamWaitEvent(st[0], e1[g], 0));   // every shard has landed before tonemap / read-back
+    if (fused) for (int g = 1; g < n; g++) {
+        CU(cudaStreamWaitEvent(st[0], e1[g], 0));   // every shard has landed (or is complete at home) before tonemap / read-back
+        if (wf && (rc = grt_internal_peer_pull(d_shared, d_sum[g], nval, st[0]))) goto done;
+    }
+    CU(cudaEventRecord(e1[0], st[0]));
     d_total = fused ? d_shared : d_sum[0];
     if (rgb8) {
         CU(grt_dev_alloc((void**)&d_rgb8, nval));
@@ -208,7 +259,7 @@ extern "C" int grt_render_multi(const GrtScene* scene, const GrtCamera* cam, con
 done:
     for (int g = 0; g < n; g++) {
         if (hs[g]) cudaSetDevice(devices[g]);
-        if (d_sum[g]) grt_dev_free(d_sum[g]);
+        if (d_sum[g]) { if (own_sum[g]) peer_buf_release(devices[g], d_sum[g], own_sum[g]); else grt_dev_free(d_sum[g]); }
         if (e0[g]) cudaEventDestroy(e0[g]);
         if (e1[g]) cudaEventDestroy(e1[g]);
         if (st[g]) cudaStreamDestroy(st[g]);

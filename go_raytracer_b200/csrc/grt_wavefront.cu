@@ -574,7 +574,7 @@ int grt_render_wavefront(GrtSceneHandle h, const GrtCamera* cam, const GrtOption
         size_t bytes = n * 16 * 5 + n * 16 * (size_t)(cam->max_depth + 1) + n * 4 * Q_COUNT + C_WORDS * 4 + 64;
         void* pinned = nullptr;
         pool = grt_internal_wf_pool(h, bytes, &pinned);
-        if (!pool) { grt_set_error("wavefront: cannot allocate the path pool"); rc = GRT_E_CUDA; goto done; }
+        if (!pool) { rc = GRT_E_CUDA; goto done; }   // (grt_internal_wf_pool has set the error text)
         h_counters = (uint32_t*)pinned;
         unsigned char* p = (unsigned char*)pool;
         P.S0 = (float4*)p; p += n * 16; P.S1 = (float4*)p; p += n * 16; P.S2 = (float4*)p; p += n * 16;
