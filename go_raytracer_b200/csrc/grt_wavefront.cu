@@ -370,8 +370,8 @@ static int wf_run(GrtSceneHandle h, WfParams& P, cudaStream_t st, uint32_t* h_co
     int rc = GRT_OK;
     // Persistent extend with dynamic ray fetch (wf_extend_dyn) vs one thread per slot (wf_extend), measured with the 4-wide
     // BVH, one primitive per leaf and lists as wide nodes (profiles/README.md, round 2): triangle meshes 462 vs 232
-    // Mpaths/s, the sphere BVH of book 1 796 vs 696, the book-2 cover 538 vs 510 — every BVH scene takes the persistent
-    // kernel now (round 1's binary tree with 4-primitive leaves had book 2 the other way round: 252 vs 311).
+    // Mpaths/s, the sphere BVH of book 1 796 vs 696, the book-2 cover 538 vs 510 (round 1's binary tree with 4-primitive
+    // leaves had book 2 the other way round: 252 vs 311).
     // Since the medium-free subtrees are regrouped by SAH (wide_bvh.hpp) book 1 visits ~7 nodes of a 140-node tree per ray:
     // that small a scene sits in shared memory whole and the plain kernel wins again (1662 vs 1547), book 2 (521 nodes, two
     // media) stays with the persistent one (743 vs 657).
