@@ -20,7 +20,12 @@
 //     exact sweep for sets of <= 16 that keeps groups of four together), straight into 4-wide nodes.  BuildBVH splits
 //     at the object median of the longest axis, which puts the 1000-unit ground sphere of the book-1 cover next to
 //     0.2-unit spheres in every upper node: regrouping cuts the box tests per segment from 73 to 24 there (+21 %
-//     paths/s) and from 62 to 54 on the 1M-triangle mesh (+7 %); GRT_WIDE_SAH=0 keeps the widened BuildBVH tree.
+//     paths/s) and from 62 to 54 on the 1M-triangle mesh (+7 %); GRT_WIDE_SAH=0 keeps the widened BuildBVH tree;
+//   * the same holds BETWEEN two media of a list: a medium test sees the closest hit among the items before it
+//     (hittable.go:129-136, medium.go:38-47) and nothing of the items after it, so every maximal run of medium-free list
+//     items is one set of surfaces, regrouped into one nearest-first subtree (nested lists and BVHs dissolved into it),
+//     while the media and the runs keep their list order.  Book 2's world list becomes [6 surfaces + 400 boxes], medium,
+//     medium, [2 spheres + 1000 spheres]: +10 % paths/s (GRT_WIDE_SAH_LISTS=0: lists keep their items one by one).
 //
 // Node layout (128 bytes = one L1 line, 8 x float4): lo.x[4] lo.y[4] lo.z[4] hi.x[4] hi.y[4] hi.z[4] ref[4] meta[4];
 // meta[0] bit 0 = children may be visited nearest first, meta[1] = number of children.  Empty slots hold the empty
@@ -35,6 +40,7 @@
 #include <deque>
 #include <functional>
 #include <limits>
+#include <map>
 #include <string>
 #include <vector>
 #include "../../include/grt.h"
@@ -151,6 +157,43 @@ class Builder {
             kids.clear();
             std::vector<Box> kbox;
             std::vector<uint32_t> kref;
+            if (wk.list && sah && sahLists) {
+                // A medium test only depends on the closest hit among the items BEFORE it (hittable.go:129-136 hands every
+                // item rayT.Max = closest so far; medium.go:38-47 clamps to it and then draws), so the items between two
+                // media are again just a set of surfaces: every maximal run of medium-free items is regrouped by SAH into
+                // one nearest-first subtree (nested lists and BVHs dissolved into it); the media and the runs keep their
+                // list order.  A list without any medium becomes that subtree itself.
+                std::vector<uint32_t>& items = wk.items;
+                std::vector<uint32_t> out;
+                size_t i = 0;
+                while (i < items.size()) {
+                    size_t j = i;
+                    while (j < items.size() && !subtreeHasMedium(items[j]) && !isSet(items[j])) j++;
+                    const bool whole = i == 0 && j == items.size();
+                    if (j - i >= 2 || (j - i == 1 && !(items[i] & GRT_DREF_RUN_BIT) && type(items[i]) == GRT_REF_LIST)) {
+                        const size_t lo = leaves.size();
+                        for (size_t k = i; k < j; k++) appendItemLeaves(items[k], 0);
+                        const size_t hi = leaves.size();
+                        if (hi - lo >= 2 && whole) {
+                            wk.list = false; wk.lo = lo; wk.hi = hi; wk.box = rangeBox(lo, hi); wk.haveBox = true;
+                            break;
+                        } else if (hi - lo >= 2) {
+                            const uint32_t cw = alloc();
+                            Work sub{false, cw, 0, {}};
+                            sub.lo = lo; sub.hi = hi; sub.box = rangeBox(lo, hi); sub.haveBox = true;
+                            setBox[cw] = sub.box;
+                            queue.push_back(std::move(sub));
+                            out.push_back(GRT_DREF_RUN_BIT | ((uint32_t)GRT_REF_NODE << GRT_REF_SHIFT) | cw);
+                        } else {
+                            leaves.resize(lo);
+                            for (size_t k = i; k < j; k++) out.push_back(items[k]);
+                        }
+                    } else for (size_t k = i; k < j; k++) out.push_back(items[k]);
+                    if (j < items.size()) { out.push_back(items[j]); j++; }
+                    i = j;
+                }
+                if (wk.list) items.swap(out);
+            }
             if (!wk.list && wk.hi == 0 && sah && !subtreeHasMedium(GRT_MAKE_REF(GRT_REF_NODE, wk.b)) && height[wk.b] >= sahMinHeight)
                 gatherLeaves(wk.b, wk.lo, wk.hi);   // a medium-free binary subtree: only its SET of leaves matters, regroup it
             if (wk.hi > wk.lo) {
@@ -256,7 +299,7 @@ class Builder {
                     Box bx = Box::none();
                     for (uint32_t it : sub) bx.add(itemBox(it));
                     if (bx.empty()) continue;
-                    if (cnt == 1) kref.push_back((sub[0] & GRT_DREF_RUN_BIT) ? sub[0] : deviceRef(sub[0]));
+                    if (cnt == 1) kref.push_back(isSet(sub[0]) ? GRT_MAKE_REF(GRT_REF_NODE, sub[0] & GRT_DREF_RUN_INDEX_MASK) : ((sub[0] & GRT_DREF_RUN_BIT) ? sub[0] : deviceRef(sub[0])));
                     else {
                         uint32_t cw = alloc();
                         queue.push_back(Work{true, cw, 0, std::move(sub)});
@@ -322,8 +365,38 @@ class Builder {
     struct SahLeaf { uint32_t ref; Box box; double c[3]; };
     std::vector<SahLeaf> leaves;
 
+    // a list item that stands for an SAH-regrouped run of medium-free items: RUN bit | NODE type | wide node index
+    int sahLists = getenv("GRT_WIDE_SAH_LISTS") ? atoi(getenv("GRT_WIDE_SAH_LISTS")) : 1;
+    std::map<uint32_t, Box> setBox;
+    static bool isSet(uint32_t it) { return (it & GRT_DREF_RUN_BIT) && ((it >> GRT_REF_SHIFT) & 7u) == GRT_REF_NODE; }
+    void pushLeaf(uint32_t ref) {
+        SahLeaf L;
+        L.ref = ref;
+        L.box = refBox(ref);
+        if (L.box.empty()) return;
+        for (int a = 0; a < 3; a++) L.c[a] = 0.5 * (L.box.lo[a] + L.box.hi[a]);
+        leaves.push_back(L);
+    }
+    // the surfaces below one medium-free list item, appended to `leaves`: runs expanded, nested lists and BVHs dissolved
+    void appendItemLeaves(uint32_t it, int depth) {
+        if (depth > 16) { pushLeaf(it); return; }
+        if (it & GRT_DREF_RUN_BIT) {
+            const uint32_t t = (it >> GRT_REF_SHIFT) & 7u, cnt = ((it >> GRT_DREF_RUN_INDEX_BITS) & 7u) + 1u, first = it & GRT_DREF_RUN_INDEX_MASK;
+            for (uint32_t j = 0; j < cnt; j++) pushLeaf(GRT_MAKE_REF(t, first + j));
+            return;
+        }
+        if (type(it) == GRT_REF_NODE && idx(it) < N.size()) { size_t lo, hi; gatherLeaves(idx(it), lo, hi, true); return; }
+        if (type(it) == GRT_REF_LIST) {
+            std::vector<uint32_t> sub;
+            listItems(idx(it), sub);
+            for (uint32_t x : sub) appendItemLeaves(x, depth + 1);
+            return;
+        }
+        if (type(it) != GRT_REF_NONE) pushLeaf(it);
+    }
+
     // the leaves of binary subtree b (remapped ABI refs that are not inner nodes of it), appended to `leaves`
-    void gatherLeaves(uint32_t b0, size_t& lo, size_t& hi) {
+    void gatherLeaves(uint32_t b0, size_t& lo, size_t& hi, bool append = false) {
         lo = leaves.size();
         std::vector<uint32_t> st{b0};
         while (!st.empty()) {
@@ -344,7 +417,7 @@ class Builder {
             }
         }
         hi = leaves.size();
-        if (hi - lo < 2) { leaves.resize(lo); hi = lo = 0; }   // nothing to regroup: the plain collapse handles it
+        if (!append && hi - lo < 2) { leaves.resize(lo); hi = lo = 0; }   // nothing to regroup: the plain collapse handles it
     }
     Box rangeBox(size_t lo, size_t hi) const {
         Box b = Box::none();
@@ -449,6 +522,7 @@ class Builder {
         }
     }
     Box itemBox(uint32_t it) const {
+        if (isSet(it)) return setBox.at(it & GRT_DREF_RUN_INDEX_MASK);
         if (it & GRT_DREF_RUN_BIT) {
             Box b = Box::none();
             const uint32_t t = (it >> GRT_REF_SHIFT) & 7u, cnt = ((it >> GRT_DREF_RUN_INDEX_BITS) & 7u) + 1u, first = it & GRT_DREF_RUN_INDEX_MASK;
