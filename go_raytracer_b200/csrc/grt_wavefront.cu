@@ -559,9 +559,10 @@ int grt_render_wavefront(GrtSceneHandle h, const GrtCamera* cam, const GrtOption
     // 1303 / 1079).
     P.exit16 = P.scene.n_nodes >= WF_DYN_TREELET_MIN_NODES ? 9 : (P.scene.n_media ? 3 : 0);
     if (const char* e = getenv("GRT_WF_EXIT16")) { int v = atoi(e); if (v >= 0 && v <= 16) P.exit16 = v; }
-    // node-step quorum: triangle meshes 8/16, scenes whose leaves are spheres / boxes / media 2/16
-    // (8 / 4 / 2 sixteenths: mesh 500 / 478 / -, book 2 634 / 653 / 660, book 1 994 / 1059 / 1070 Mpaths/s)
-    P.vote16 = (P.scene.n_tris > P.scene.n_spheres + P.scene.n_boxes) ? 10 : 2;
+    // node-step quorum: triangle meshes 10/16, scenes whose leaves are spheres / boxes / media 4/16
+    // (mesh, 6 / 8 / 10 / 12 / 14 sixteenths: 514 / 520 / 530 / 522 / 499; book 2 on its final tree, 1 / 2 / 4: 803 / 819 / 833;
+    // on the earlier trees 2 / 4 / 8: 660 / 653 / 634)
+    P.vote16 = (P.scene.n_tris > P.scene.n_spheres + P.scene.n_boxes) ? 10 : 4;
     if (const char* e = getenv("GRT_WF_VOTE16")) { int v = atoi(e); if (v >= 1 && v <= 16) P.vote16 = v; }
     void* pool = nullptr;
     uint32_t* h_counters = nullptr;
