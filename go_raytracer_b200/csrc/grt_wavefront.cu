@@ -555,9 +555,10 @@ int grt_render_wavefront(GrtSceneHandle h, const GrtCamera* cam, const GrtOption
     // of the lanes that entered still have work.  A refill costs a pass of atomics, ray fetches and stack resets, so it
     // only pays where traversal lengths differ a lot: the 1M-triangle mesh 9/16 (2 / 4 / 6 / 8 / 9 / 10 / 12: 445 / 484 /
     // 509 / 518 / 522 / 519 / 497 Mpaths/s), book 2 with its media 3/16 (0 / 2 / 3 / 4 / 8 / 12: 718 / 737 / 743 / 745 /
-    // 720 / 658), book 1's 140-node tree runs every ray of the warp to its end (0 / 2 / 4 / 8 / 12: 1544 / 1470 / 1409 /
-    // 1303 / 1079).
-    P.exit16 = P.scene.n_nodes >= WF_DYN_TREELET_MIN_NODES ? 9 : (P.scene.n_media ? 3 : 0);
+    // 720 / 658); book 1's 140-node tree would run every ray of the warp to its end (0 / 2 / 4 / 8 / 12: 1544 / 1470 / 1409 /
+    // 1303 / 1079) but takes the plain kernel anyway (wf_run).
+    // Meshes of every size want the refill (2 k / 32 k triangles: 659 / 454 Mpaths/s with 0, 749 / 531 with 6, 708 / 541 with 9).
+    P.exit16 = (P.scene.n_tris > P.scene.n_spheres + P.scene.n_boxes) ? 9 : 3;
     if (const char* e = getenv("GRT_WF_EXIT16")) { int v = atoi(e); if (v >= 0 && v <= 16) P.exit16 = v; }
     // node-step quorum: triangle meshes 10/16, scenes whose leaves are spheres / boxes / media 4/16
     // (mesh, 6 / 8 / 10 / 12 / 14 sixteenths: 514 / 520 / 530 / 522 / 499; book 2 on its final tree, 1 / 2 / 4: 803 / 819 / 833;

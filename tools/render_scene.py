@@ -14,6 +14,8 @@ if sid in (2, 5):
     kw["image"] = np.load("tests/golden/earthmap_rgb8.npz")["rgb"]
 if sid == 2 and width:
     kw["aspect"] = 16 / 9
+if sid == 8 and os.environ.get("MESH_SEGMENTS"):   # smaller meshes than config C5's 708 x 708 segments
+    kw["mesh_segments"] = int(os.environ["MESH_SEGMENTS"])
 s, cfg = g.builtin_scene(sid, width=width, spp=spp, **kw)
 dev = g.DeviceScene(s, 0, cw, cl)
 cam = g.derive_camera(cfg)
